@@ -1,0 +1,718 @@
+// nint_api.cu — the C ABI of include/ninterp_cuda.h: handle life cycle, the reference's
+// validation rules, the axis pack (nodes + bucket tables) and the host-buffer pipeline.
+//
+// Reference items mirrored here (paths relative to the reference's src/):
+//   InterpData::validate       interpolator/data.rs:69-89
+//   InterpDataND::validate     interpolator/n/mod.rs:71-101, ndim() :104-110
+//   check_extrapolate          interpolator/mod.rs:83-107
+//   Interpolator::interpolate  interpolator/{one,two,three,n}/mod.rs (point-length check)
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "nint_device.cuh"
+
+namespace nint {
+std::atomic<unsigned long long> g_launch_count{0};
+}
+
+namespace {
+
+thread_local std::string t_err_msg;
+thread_local int t_err_dim = -1;
+
+int fail(int code, int dim, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_err_msg = buf;
+    t_err_dim = dim;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(NINT_E_CUDA, -1, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+}
+
+#define NINT_CUDA(call)                                   \
+    do {                                                  \
+        cudaError_t e__ = (call);                         \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+size_t elem_size(int dtype) { return dtype == NINT_F64 ? 8 : 4; }
+
+double load_elem(int dtype, const void* p, size_t i) {
+    return dtype == NINT_F64 ? ((const double*)p)[i] : (double)((const float*)p)[i];
+}
+
+const char* extrap_name(int e) {
+    switch (e) {
+    case NINT_EXTRAPOLATE_ENABLE: return "Enable";
+    case NINT_EXTRAPOLATE_FILL: return "Fill";
+    case NINT_EXTRAPOLATE_CLAMP: return "Clamp";
+    case NINT_EXTRAPOLATE_WRAP: return "Wrap";
+    default: return "Error";
+    }
+}
+
+struct AxisMeta {
+    int L = 0, M = 0;
+    unsigned node_off = 0, lut_off = 0;
+    double g0 = 0, gl = 0, inv_w = 0;
+    long long vstride = 0;
+};
+
+// Device buffers of one in-flight chunk of the host pipeline.
+struct Slot {
+    void* d_in = nullptr;  // chunk * ndim * sizeof(T)
+    void* d_out = nullptr;
+    uint8_t* d_status = nullptr;
+    cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
+};
+
+struct Pipeline {
+    static constexpr int kSlots = 3;
+    size_t chunk = 0;  // points per chunk
+    Slot slot[kSlots];
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    bool ready = false;
+};
+
+}  // namespace
+
+struct nint_handle {
+    int device = 0, kind = 0, dtype = 0, strategy = 0, extrap = 0;
+    int ngrid = 0, nvalue_dim = 0;
+    int ndim_eff = 0;       // Interpolator::ndim()
+    bool constant = false;  // 0-D InterpND
+    std::vector<size_t> axis_len, value_shape;
+    std::vector<std::vector<unsigned char>> axes_host;
+    double fill = 0.0;  // value of Fill(v), exact in T
+    size_t values_len = 1;
+    void* d_values = nullptr;
+    unsigned char* d_pack = nullptr;
+    unsigned pack_bytes = 0;
+    bool smem_axes = true;
+    AxisMeta ax[NINT_MAX_NDIM];
+    int sm_count = 0;
+    // scratch for the synchronous entry points
+    nint_batch_info* d_info = nullptr;
+    void* d_pt = nullptr;   // one point
+    void* d_res = nullptr;  // one value + status byte
+    Pipeline pipe;
+    std::mutex mu;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------- validation
+int check_extrapolate(const nint_handle* h, int current, int requested) {
+    // interpolator/mod.rs:88
+    if (requested == NINT_EXTRAPOLATE_ENABLE && h->strategy != NINT_LINEAR)
+        return fail(NINT_E_EXTRAPOLATE_SELECTION, -1,
+                    "selected `Extrapolate` variant (%s) is unimplemented/inapplicable for interpolator",
+                    extrap_name(current));
+    // interpolator/mod.rs:97-104 — reads self.extrapolate, not the argument
+    if (current == NINT_EXTRAPOLATE_ENABLE) {
+        for (int i = 0; i < h->ngrid; ++i)
+            if (h->axis_len[i] < 2)
+                return fail(NINT_E_OTHER, i, "at least 2 data points are required for extrapolation: dim %d", i);
+    }
+    return NINT_OK;
+}
+
+int validate_data(const nint_handle* h) {
+    size_t n = (size_t)h->nvalue_dim;
+    if (h->kind == NINT_KIND_ND) {
+        const size_t nd = (h->values_len == 1) ? 0 : (size_t)h->nvalue_dim;  // n/mod.rs:104-110
+        bool all_empty = true;
+        for (int i = 0; i < h->ngrid; ++i) all_empty = all_empty && h->axis_len[i] == 0;
+        if ((size_t)h->ngrid != nd && !(nd == 0 && all_empty))  // n/mod.rs:76-83
+            return fail(NINT_E_OTHER, -1, "grid length %d does not match dimensionality %zu", h->ngrid, nd);
+        n = nd;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        const size_t len = h->axis_len[i];
+        if (len == 0)  // data.rs:76
+            return fail(NINT_E_EMPTY_GRID, (int)i, "supplied grid coordinates cannot be empty: dim %zu", i);
+        const void* g = h->axes_host[i].data();
+        for (size_t k = 0; k + 1 < len; ++k) {
+            if (!(load_elem(h->dtype, g, k) <= load_elem(h->dtype, g, k + 1)))  // data.rs:80
+                return fail(NINT_E_MONOTONICITY, (int)i,
+                            "supplied coordinates must be sorted and non-repeating: dim %zu", i);
+        }
+        if (len != h->value_shape[i])  // data.rs:84
+            return fail(NINT_E_INCOMPATIBLE_SHAPES, (int)i,
+                        "supplied grid and values are not compatible shapes: dim %zu", i);
+    }
+    return NINT_OK;
+}
+
+// ------------------------------------------------------------------------------- axis pack
+unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
+
+// Bucket table of one axis.  Bucket b of width w_eff covers [g0 + b*w_eff, g0 + (b+1)*w_eff); a point
+// that the device maps to bucket b lies, with rounding, inside buckets b-1..b+1, so its node count
+// c = #{g < p} satisfies K[b-1] <= c <= K[b+2] where K[j] = #{g < edge j}.
+void build_lut(int dtype, const void* nodes, int L, int M, double g0, double inv_w_eff, std::vector<uint2>& lut) {
+    lut.resize(M);
+    if (M == 1) {
+        lut[0] = make_uint2(0u, (unsigned)L);
+        return;
+    }
+    // work with offsets from the first node, as the device does: (g - g0) is accurate to a relative
+    // 2^-53 of the span, far below one bucket, whatever the magnitude of g0
+    std::vector<double> rel(L);
+    for (int i = 0; i < L; ++i) rel[i] = load_elem(dtype, nodes, i) - g0;
+    const double w = 1.0 / inv_w_eff;
+    std::vector<unsigned> K(M + 1);
+    for (int j = 0; j <= M; ++j) {
+        const double edge = (double)j * w;
+        K[j] = (unsigned)(std::lower_bound(rel.begin(), rel.end(), edge) - rel.begin());
+    }
+    for (int b = 0; b < M; ++b) {
+        const unsigned lo = (b == 0) ? 0u : K[b - 1];
+        const unsigned hi = (b + 2 >= M) ? (unsigned)L : K[b + 2];
+        lut[b] = make_uint2(lo, std::max(hi, lo));
+    }
+}
+
+constexpr unsigned kSmemPreferred = 64u * 1024u;   // keeps several CTAs resident per SM
+constexpr unsigned kSmemLimit = 200u * 1024u;      // below the 227 KB opt-in ceiling
+
+int build_pack(nint_handle* h) {
+    const int n = h->ndim_eff;
+    const size_t es = elem_size(h->dtype);
+    // choose bucket counts: 2 per cell if it fits comfortably, fewer otherwise
+    auto total_bytes = [&](double per_cell) {
+        unsigned long long t = 0;
+        for (int d = 0; d < n; ++d) {
+            const unsigned long long L = h->axis_len[d];
+            unsigned long long M = std::max<unsigned long long>(1, (unsigned long long)(per_cell * (double)L));
+            t += align_up((unsigned)(L * es), 16) + M * 8ull;
+        }
+        return t;
+    };
+    double per_cell = 2.0;
+    unsigned long long nodes_only = total_bytes(0.0);
+    if (nodes_only > kSmemLimit) {
+        h->smem_axes = false;  // axes live in global memory (L1/L2-cached); tables can be generous
+        per_cell = 2.0;
+    } else {
+        h->smem_axes = true;
+        while (per_cell > 1.0 / 64 && total_bytes(per_cell) > kSmemPreferred) per_cell *= 0.5;
+        if (total_bytes(per_cell) > kSmemLimit) per_cell = 0.0;
+    }
+    std::vector<unsigned char> pack;
+    for (int d = 0; d < n; ++d) {
+        AxisMeta& a = h->ax[d];
+        const int L = (int)h->axis_len[d];
+        const void* nodes = h->axes_host[d].data();
+        a.L = L;
+        a.g0 = load_elem(h->dtype, nodes, 0);
+        a.gl = load_elem(h->dtype, nodes, L - 1);
+        int M = (int)std::min<double>(std::max(1.0, per_cell * (double)L), h->dtype == NINT_F64 ? 16777216.0 : 1048576.0);
+        double inv_w = 0.0;
+        const double span = a.gl - a.g0;
+        if (L >= 2 && M >= 2 && std::isfinite(span) && span > 0.0) {
+            inv_w = (double)M / span;
+            if (h->dtype == NINT_F32) inv_w = (double)(float)inv_w;  // the device multiplies by this in T
+            const double w = 1.0 / inv_w;
+            if (!std::isfinite(inv_w) || !(inv_w > 0.0) || !std::isfinite(w) || !(w > 0.0)) inv_w = 0.0;
+        }
+        if (inv_w == 0.0) M = 1;  // degenerate axis: one bucket, plain binary search over all nodes
+        a.M = M;
+        a.inv_w = inv_w;
+        std::vector<uint2> lut;
+        build_lut(h->dtype, nodes, L, M, a.g0, inv_w, lut);
+        a.node_off = (unsigned)pack.size();
+        pack.resize(pack.size() + align_up((unsigned)(L * es), 16), 0);
+        std::memcpy(pack.data() + a.node_off, nodes, (size_t)L * es);
+        a.lut_off = (unsigned)pack.size();
+        pack.resize(pack.size() + align_up((unsigned)(M * 8), 16), 0);
+        std::memcpy(pack.data() + a.lut_off, lut.data(), (size_t)M * 8);
+    }
+    h->pack_bytes = (unsigned)pack.size();
+    if (h->pack_bytes == 0) return NINT_OK;
+    if (h->smem_axes && h->pack_bytes > 220u * 1024u) h->smem_axes = false;
+    NINT_CUDA(cudaMalloc((void**)&h->d_pack, h->pack_bytes));
+    NINT_CUDA(cudaMemcpy(h->d_pack, pack.data(), h->pack_bytes, cudaMemcpyHostToDevice));
+    return NINT_OK;
+}
+
+// ------------------------------------------------------------------------------- value table
+int upload_values(nint_handle* h, const void* values_host, const ptrdiff_t* strides) {
+    const size_t es = elem_size(h->dtype);
+    const int nd = h->nvalue_dim;
+    bool dense = true;
+    if (strides) {
+        ptrdiff_t expect = 1;
+        for (int d = nd - 1; d >= 0; --d) {
+            if (h->value_shape[d] > 1 && strides[d] != expect) dense = false;
+            expect *= (ptrdiff_t)h->value_shape[d];
+        }
+    }
+    NINT_CUDA(cudaMalloc(&h->d_values, std::max<size_t>(h->values_len, 1) * es));
+    if (dense) {
+        NINT_CUDA(cudaMemcpy(h->d_values, values_host, h->values_len * es, cudaMemcpyHostToDevice));
+        return NINT_OK;
+    }
+    // strided ArrayView (data.rs:92-97): gather into C order, then upload
+    std::vector<unsigned char> tmp(h->values_len * es);
+    std::vector<size_t> idx(nd, 0);
+    const unsigned char* src = (const unsigned char*)values_host;
+    for (size_t lin = 0; lin < h->values_len; ++lin) {
+        ptrdiff_t off = 0;
+        for (int d = 0; d < nd; ++d) off += (ptrdiff_t)idx[d] * strides[d];
+        std::memcpy(tmp.data() + lin * es, src + off * (ptrdiff_t)es, es);
+        for (int d = nd - 1; d >= 0; --d) {
+            if (++idx[d] < h->value_shape[d]) break;
+            idx[d] = 0;
+        }
+    }
+    NINT_CUDA(cudaMemcpy(h->d_values, tmp.data(), tmp.size(), cudaMemcpyHostToDevice));
+    return NINT_OK;
+}
+
+// ------------------------------------------------------------------------------- launching
+template <class T>
+void fill_params(const nint_handle* h, nint::Params<T>& P) {
+    std::memset(&P, 0, sizeof P);
+    P.values = (const T*)h->d_values;
+    P.pack = h->d_pack;
+    P.pack_bytes = h->pack_bytes;
+    P.fill = (T)h->fill;
+    P.extrap = h->extrap;
+    for (int d = 0; d < h->ndim_eff; ++d) {
+        const AxisMeta& a = h->ax[d];
+        P.L[d] = a.L;
+        P.M[d] = a.M;
+        P.node_off[d] = a.node_off;
+        P.lut_off[d] = a.lut_off;
+        P.vstride[d] = a.vstride;
+        P.g0[d] = (T)a.g0;
+        P.gl[d] = (T)a.gl;
+        P.inv_w[d] = (T)a.inv_w;
+    }
+}
+
+template <class T>
+int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride, size_t n, void* out,
+                 uint8_t* status, nint_batch_info* info_dev, unsigned long long index_base, cudaStream_t stream) {
+    if (h->constant) {
+        cudaError_t e = nint::launch_constant<T>((const T*)h->d_values, (T*)out, status, n, h->sm_count, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "constant kernel launch");
+        return NINT_OK;
+    }
+    nint::Params<T> P;
+    fill_params<T>(h, P);
+    for (int d = 0; d < h->ndim_eff; ++d) P.coords[d] = (const T*)cols[d];
+    P.coord_stride = coord_stride;
+    P.out = (T*)out;
+    P.status = status;
+    P.info = info_dev;
+    P.n = n;
+    P.index_base = index_base;
+    nint::LaunchCfg cfg;
+    cfg.ndim = h->ndim_eff;
+    cfg.is_nd = h->kind == NINT_KIND_ND;
+    cfg.strategy = h->strategy;
+    cfg.extrap = h->extrap;
+    cfg.smem_axes = h->smem_axes;
+    cfg.smem_bytes = h->pack_bytes;
+    cfg.sm_count = h->sm_count;
+    cfg.stream = stream;
+    cudaError_t e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : nint::launch_fixed<T>(P, cfg);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    return NINT_OK;
+}
+
+int launch(nint_handle* h, const void* const* cols, long long coord_stride, size_t n, void* out, uint8_t* status,
+           nint_batch_info* info_dev, unsigned long long index_base, cudaStream_t stream) {
+    if (n == 0) return NINT_OK;
+    if (h->dtype == NINT_F64)
+        return launch_typed<double>(h, cols, coord_stride, n, out, status, info_dev, index_base, stream);
+    return launch_typed<float>(h, cols, coord_stride, n, out, status, info_dev, index_base, stream);
+}
+
+int reset_info(nint_batch_info* info_dev, cudaStream_t stream) {
+    NINT_CUDA(cudaMemsetAsync(info_dev, 0, 2 * sizeof(uint64_t), stream));
+    NINT_CUDA(cudaMemsetAsync((unsigned char*)info_dev + 2 * sizeof(uint64_t), 0xFF, 2 * sizeof(uint64_t), stream));
+    return NINT_OK;
+}
+
+void split_cols(const nint_handle* h, const void* base, long long* stride, const void** cols) {
+    const size_t es = elem_size(h->dtype);
+    for (int d = 0; d < h->ndim_eff; ++d) cols[d] = (const unsigned char*)base + (size_t)d * es;
+    *stride = h->ndim_eff;
+}
+
+int ensure_pipeline(nint_handle* h) {
+    Pipeline& p = h->pipe;
+    if (p.ready) return NINT_OK;
+    const size_t es = elem_size(h->dtype);
+    p.chunk = (size_t)4 << 20;  // points per chunk: ~100 MB in flight per slot for 3-D f64
+    NINT_CUDA(cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking));
+    NINT_CUDA(cudaStreamCreateWithFlags(&p.s_k, cudaStreamNonBlocking));
+    NINT_CUDA(cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));
+    for (Slot& s : p.slot) {
+        NINT_CUDA(cudaMalloc(&s.d_in, p.chunk * (size_t)std::max(h->ndim_eff, 1) * es));
+        NINT_CUDA(cudaMalloc(&s.d_out, p.chunk * es));
+        NINT_CUDA(cudaMalloc((void**)&s.d_status, p.chunk));
+        NINT_CUDA(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
+        NINT_CUDA(cudaEventCreateWithFlags(&s.k_done, cudaEventDisableTiming));
+        NINT_CUDA(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
+    }
+    p.ready = true;
+    return NINT_OK;
+}
+
+void free_pipeline(nint_handle* h) {
+    Pipeline& p = h->pipe;
+    for (Slot& s : p.slot) {
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.d_status) cudaFree(s.d_status);
+        if (s.in_done) cudaEventDestroy(s.in_done);
+        if (s.k_done) cudaEventDestroy(s.k_done);
+        if (s.out_done) cudaEventDestroy(s.out_done);
+    }
+    if (p.s_in) cudaStreamDestroy(p.s_in);
+    if (p.s_k) cudaStreamDestroy(p.s_k);
+    if (p.s_out) cudaStreamDestroy(p.s_out);
+    p = Pipeline();
+}
+
+}  // namespace
+
+// ==================================================================================== C ABI
+extern "C" {
+
+int nint_create(int device, int kind, int dtype, int ngrid, const size_t* axis_len, const void* const* axes_host,
+                int nvalue_dim, const size_t* value_shape, const void* values_host,
+                const ptrdiff_t* value_strides, int strategy, int extrapolate, const void* fill,
+                nint_handle** out) {
+    if (!out) return fail(NINT_E_INVALID_ARGUMENT, -1, "out handle pointer is NULL");
+    *out = nullptr;
+    if (dtype != NINT_F32 && dtype != NINT_F64) return fail(NINT_E_INVALID_ARGUMENT, -1, "unknown dtype %d", dtype);
+    if (kind != NINT_KIND_FIXED && kind != NINT_KIND_ND) return fail(NINT_E_INVALID_ARGUMENT, -1, "unknown kind %d", kind);
+    if (strategy < NINT_LINEAR || strategy > NINT_RIGHT_NEAREST)
+        return fail(NINT_E_INVALID_ARGUMENT, -1, "unknown strategy %d", strategy);
+    if (extrapolate < NINT_EXTRAPOLATE_ENABLE || extrapolate > NINT_EXTRAPOLATE_ERROR)
+        return fail(NINT_E_INVALID_ARGUMENT, -1, "unknown extrapolate %d", extrapolate);
+    if (ngrid < 0 || nvalue_dim < 0 || (ngrid > 0 && !axis_len) || (nvalue_dim > 0 && !value_shape))
+        return fail(NINT_E_INVALID_ARGUMENT, -1, "bad grid/value rank arguments");
+    if (kind == NINT_KIND_FIXED && (ngrid != nvalue_dim || ngrid < 1 || ngrid > 3))
+        return fail(NINT_E_INVALID_ARGUMENT, -1, "Interp1D/2D/3D need 1..3 axes and a value array of the same rank");
+    if ((strategy == NINT_LEFT_NEAREST || strategy == NINT_RIGHT_NEAREST) && !(kind == NINT_KIND_FIXED && ngrid == 1))
+        return fail(NINT_E_UNSUPPORTED, -1, "LeftNearest/RightNearest exist for Interp1D only");
+    if (extrapolate == NINT_EXTRAPOLATE_FILL && !fill) return fail(NINT_E_INVALID_ARGUMENT, -1, "Fill needs a value");
+
+    nint_handle* h = new nint_handle();
+    h->device = device;
+    h->kind = kind;
+    h->dtype = dtype;
+    h->strategy = strategy;
+    h->extrap = extrapolate;
+    h->ngrid = ngrid;
+    h->nvalue_dim = nvalue_dim;
+    const size_t es = elem_size(dtype);
+    if (extrapolate == NINT_EXTRAPOLATE_FILL) h->fill = load_elem(dtype, fill, 0);
+    h->values_len = 1;
+    for (int i = 0; i < nvalue_dim; ++i) {
+        h->value_shape.push_back(value_shape[i]);
+        h->values_len *= value_shape[i];
+    }
+    for (int i = 0; i < ngrid; ++i) {
+        h->axis_len.push_back(axis_len[i]);
+        std::vector<unsigned char> a(axis_len[i] * es);
+        if (axis_len[i]) {
+            if (!axes_host || !axes_host[i]) {
+                delete h;
+                return fail(NINT_E_INVALID_ARGUMENT, i, "axis %d has %zu nodes but no data pointer", i, axis_len[i]);
+            }
+            std::memcpy(a.data(), axes_host[i], a.size());
+        }
+        h->axes_host.push_back(std::move(a));
+    }
+    // `InterpXD::new`: data.validate() first, then check_extrapolate (three/mod.rs:137-143)
+    int rc = validate_data(h);
+    if (rc == NINT_OK) rc = check_extrapolate(h, h->extrap, h->extrap);
+    if (rc != NINT_OK) {
+        delete h;
+        return rc;
+    }
+    h->constant = (kind == NINT_KIND_ND && h->values_len == 1);
+    h->ndim_eff = h->constant ? 0 : nvalue_dim;
+    if (h->ndim_eff > NINT_MAX_NDIM) {
+        delete h;
+        return fail(NINT_E_UNSUPPORTED, -1, "ndim %d exceeds NINT_MAX_NDIM (%d)", nvalue_dim, NINT_MAX_NDIM);
+    }
+    if (!values_host && h->values_len) {
+        delete h;
+        return fail(NINT_E_INVALID_ARGUMENT, -1, "values pointer is NULL");
+    }
+    for (int d = 0; d < h->ndim_eff; ++d) {
+        if (h->axis_len[d] > (size_t)std::numeric_limits<int>::max() / 4) {
+            delete h;
+            return fail(NINT_E_UNSUPPORTED, d, "axis %d is too long", d);
+        }
+    }
+    long long stride = 1;
+    for (int d = h->ndim_eff - 1; d >= 0; --d) {
+        h->ax[d].vstride = stride;
+        stride *= (long long)h->value_shape[d];
+    }
+
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        delete h;
+        return fail(NINT_E_CUDA, -1, "cannot select CUDA device %d (no CPU fallback exists)", device);
+    }
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete h;
+        return cuda_fail(e, "cudaGetDeviceProperties");
+    }
+    h->sm_count = prop.multiProcessorCount;
+    rc = upload_values(h, values_host, value_strides);
+    if (rc == NINT_OK && !h->constant) rc = build_pack(h);
+    if (rc == NINT_OK) {
+        cudaError_t e2 = cudaMalloc((void**)&h->d_info, sizeof(nint_batch_info));
+        if (e2 == cudaSuccess) e2 = cudaMalloc(&h->d_pt, NINT_MAX_NDIM * sizeof(double));
+        if (e2 == cudaSuccess) e2 = cudaMalloc(&h->d_res, 16);
+        if (e2 != cudaSuccess) rc = cuda_fail(e2, "cudaMalloc");
+    }
+    if (rc != NINT_OK) {
+        nint_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return NINT_OK;
+}
+
+void nint_destroy(nint_handle* h) {
+    if (!h) return;
+    {
+        DeviceGuard guard(h->device);
+        free_pipeline(h);
+        if (h->d_values) cudaFree(h->d_values);
+        if (h->d_pack) cudaFree(h->d_pack);
+        if (h->d_info) cudaFree(h->d_info);
+        if (h->d_pt) cudaFree(h->d_pt);
+        if (h->d_res) cudaFree(h->d_res);
+    }
+    delete h;
+}
+
+int nint_ndim(const nint_handle* h) { return h ? h->ndim_eff : NINT_E_INVALID_ARGUMENT; }
+
+int nint_validate(nint_handle* h) {
+    if (!h) return fail(NINT_E_INVALID_ARGUMENT, -1, "handle is NULL");
+    // three/mod.rs:186-191: check_extrapolate, then data.validate()
+    int rc = check_extrapolate(h, h->extrap, h->extrap);
+    if (rc == NINT_OK) rc = validate_data(h);
+    return rc;
+}
+
+int nint_set_extrapolate(nint_handle* h, int extrapolate, const void* fill) {
+    if (!h) return fail(NINT_E_INVALID_ARGUMENT, -1, "handle is NULL");
+    if (extrapolate < NINT_EXTRAPOLATE_ENABLE || extrapolate > NINT_EXTRAPOLATE_ERROR)
+        return fail(NINT_E_INVALID_ARGUMENT, -1, "unknown extrapolate %d", extrapolate);
+    if (extrapolate == NINT_EXTRAPOLATE_FILL && !fill) return fail(NINT_E_INVALID_ARGUMENT, -1, "Fill needs a value");
+    if (h->constant) return NINT_OK;  // zero/mod.rs:60-63 and 0-D InterpND: nothing to check against
+    int rc = check_extrapolate(h, h->extrap, extrapolate);  // three/mod.rs:240-244
+    if (rc != NINT_OK) return rc;
+    h->extrap = extrapolate;
+    if (extrapolate == NINT_EXTRAPOLATE_FILL) h->fill = load_elem(h->dtype, fill, 0);
+    return NINT_OK;
+}
+
+int nint_set_strategy(nint_handle* h, int strategy) {
+    if (!h) return fail(NINT_E_INVALID_ARGUMENT, -1, "handle is NULL");
+    if (strategy < NINT_LINEAR || strategy > NINT_RIGHT_NEAREST)
+        return fail(NINT_E_INVALID_ARGUMENT, -1, "unknown strategy %d", strategy);
+    if ((strategy == NINT_LEFT_NEAREST || strategy == NINT_RIGHT_NEAREST) &&
+        !(h->kind == NINT_KIND_FIXED && h->ngrid == 1))
+        return fail(NINT_E_UNSUPPORTED, -1, "LeftNearest/RightNearest exist for Interp1D only");
+    // three/mod.rs:259-271: the strategy is replaced first, then checked (and stays replaced on error)
+    h->strategy = strategy;
+    return check_extrapolate(h, h->extrap, h->extrap);
+}
+
+int nint_interpolate_batch(nint_handle* h, const void* const* coords, size_t n, void* out, uint8_t* status,
+                           nint_batch_info* info_dev, void* stream) {
+    if (!h) return fail(NINT_E_INVALID_ARGUMENT, -1, "handle is NULL");
+    if (n == 0) return NINT_OK;
+    if (!out || (h->ndim_eff > 0 && !coords)) return fail(NINT_E_INVALID_ARGUMENT, -1, "NULL batch pointer");
+    for (int d = 0; d < h->ndim_eff; ++d)
+        if (!coords[d]) return fail(NINT_E_POINT_LENGTH, d, "supplied point slice should have length %d for %d-D interpolation", h->ndim_eff, h->ndim_eff);
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(NINT_E_CUDA, -1, "cannot select CUDA device %d", h->device);
+    if (info_dev) {
+        int rc = reset_info(info_dev, (cudaStream_t)stream);
+        if (rc != NINT_OK) return rc;
+    }
+    return launch(h, coords, 1, n, out, status, info_dev, 0, (cudaStream_t)stream);
+}
+
+int nint_interpolate_batch_aos(nint_handle* h, const void* points, size_t n, void* out, uint8_t* status,
+                               nint_batch_info* info_dev, void* stream) {
+    if (!h) return fail(NINT_E_INVALID_ARGUMENT, -1, "handle is NULL");
+    if (n == 0) return NINT_OK;
+    if (!out || (h->ndim_eff > 0 && !points)) return fail(NINT_E_INVALID_ARGUMENT, -1, "NULL batch pointer");
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(NINT_E_CUDA, -1, "cannot select CUDA device %d", h->device);
+    if (info_dev) {
+        int rc = reset_info(info_dev, (cudaStream_t)stream);
+        if (rc != NINT_OK) return rc;
+    }
+    const void* cols[NINT_MAX_NDIM] = {};
+    long long stride = 1;
+    split_cols(h, points, &stride, cols);
+    return launch(h, cols, stride, n, out, status, info_dev, 0, (cudaStream_t)stream);
+}
+
+int nint_interpolate_batch_host(nint_handle* h, int layout, const void* data, size_t n, void* out_host,
+                                uint8_t* status_host, nint_batch_info* info_host) {
+    if (!h) return fail(NINT_E_INVALID_ARGUMENT, -1, "handle is NULL");
+    if (layout != NINT_LAYOUT_SOA && layout != NINT_LAYOUT_AOS)
+        return fail(NINT_E_INVALID_ARGUMENT, -1, "unknown layout %d", layout);
+    if (info_host) *info_host = nint_batch_info{0, 0, UINT64_MAX, UINT64_MAX};
+    if (n == 0) return NINT_OK;
+    if (!out_host || (h->ndim_eff > 0 && !data)) return fail(NINT_E_INVALID_ARGUMENT, -1, "NULL batch pointer");
+    const int nd = h->ndim_eff;
+    const size_t es = elem_size(h->dtype);
+    const void* const* cols_host = (const void* const*)data;
+    if (layout == NINT_LAYOUT_SOA)
+        for (int d = 0; d < nd; ++d)
+            if (!cols_host[d]) return fail(NINT_E_POINT_LENGTH, d, "supplied point slice should have length %d for %d-D interpolation", nd, nd);
+
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(NINT_E_CUDA, -1, "cannot select CUDA device %d", h->device);
+    int rc = ensure_pipeline(h);
+    if (rc != NINT_OK) return rc;
+    Pipeline& p = h->pipe;
+    rc = reset_info(h->d_info, p.s_k);
+    if (rc != NINT_OK) return rc;
+
+    size_t j = 0;
+    for (size_t start = 0; start < n; start += p.chunk, ++j) {
+        const size_t m = std::min(p.chunk, n - start);
+        Slot& s = p.slot[j % Pipeline::kSlots];
+        // the slot's input buffer is free once its previous kernel has run, its output buffers once
+        // their previous copy-out has finished
+        if (j >= (size_t)Pipeline::kSlots) {
+            NINT_CUDA(cudaStreamWaitEvent(p.s_in, s.k_done, 0));
+            NINT_CUDA(cudaStreamWaitEvent(p.s_k, s.out_done, 0));
+        }
+        const void* cols_dev[NINT_MAX_NDIM] = {};
+        long long stride = 1;
+        if (layout == NINT_LAYOUT_AOS) {
+            NINT_CUDA(cudaMemcpyAsync(s.d_in, (const unsigned char*)data + start * (size_t)nd * es, m * (size_t)nd * es,
+                                      cudaMemcpyHostToDevice, p.s_in));
+            split_cols(h, s.d_in, &stride, cols_dev);
+        } else {
+            for (int d = 0; d < nd; ++d) {
+                unsigned char* dst = (unsigned char*)s.d_in + (size_t)d * p.chunk * es;
+                NINT_CUDA(cudaMemcpyAsync(dst, (const unsigned char*)cols_host[d] + start * es, m * es,
+                                          cudaMemcpyHostToDevice, p.s_in));
+                cols_dev[d] = dst;
+            }
+        }
+        NINT_CUDA(cudaEventRecord(s.in_done, p.s_in));
+        NINT_CUDA(cudaStreamWaitEvent(p.s_k, s.in_done, 0));
+        rc = launch(h, cols_dev, stride, m, s.d_out, status_host ? s.d_status : nullptr, h->d_info, start, p.s_k);
+        if (rc != NINT_OK) return rc;
+        NINT_CUDA(cudaEventRecord(s.k_done, p.s_k));
+        NINT_CUDA(cudaStreamWaitEvent(p.s_out, s.k_done, 0));
+        NINT_CUDA(cudaMemcpyAsync((unsigned char*)out_host + start * es, s.d_out, m * es, cudaMemcpyDeviceToHost, p.s_out));
+        if (status_host)
+            NINT_CUDA(cudaMemcpyAsync(status_host + start, s.d_status, m, cudaMemcpyDeviceToHost, p.s_out));
+        NINT_CUDA(cudaEventRecord(s.out_done, p.s_out));
+    }
+    nint_batch_info info;
+    NINT_CUDA(cudaStreamSynchronize(p.s_out));
+    NINT_CUDA(cudaMemcpyAsync(&info, h->d_info, sizeof info, cudaMemcpyDeviceToHost, p.s_k));
+    NINT_CUDA(cudaStreamSynchronize(p.s_k));
+    if (info_host) *info_host = info;
+    if (info.n_panic)
+        return fail(NINT_E_PANIC, -1, "the reference implementation would panic on %llu point(s), first at index %llu",
+                    (unsigned long long)info.n_panic, (unsigned long long)info.first_panic);
+    if (info.n_error)
+        return fail(NINT_E_EXTRAPOLATE, -1,
+                    "attempted to interpolate at point beyond grid data: %llu point(s), first at index %llu",
+                    (unsigned long long)info.n_error, (unsigned long long)info.first_error);
+    return NINT_OK;
+}
+
+int nint_interpolate(nint_handle* h, const void* point, size_t point_len, void* out) {
+    if (!h) return fail(NINT_E_INVALID_ARGUMENT, -1, "handle is NULL");
+    const int nd = h->ndim_eff;
+    if (point_len != (size_t)nd)  // three/mod.rs:194-196, n/mod.rs:288-290, zero/mod.rs:52-54
+        return fail(NINT_E_POINT_LENGTH, -1, "supplied point slice should have length %d for %d-D interpolation", nd, nd);
+    if (!out || (nd > 0 && !point)) return fail(NINT_E_INVALID_ARGUMENT, -1, "NULL pointer");
+    const size_t es = elem_size(h->dtype);
+    std::lock_guard<std::mutex> lock(h->mu);
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(NINT_E_CUDA, -1, "cannot select CUDA device %d", h->device);
+    cudaStream_t st = cudaStreamPerThread;
+    if (nd) NINT_CUDA(cudaMemcpyAsync(h->d_pt, point, (size_t)nd * es, cudaMemcpyHostToDevice, st));
+    const void* cols[NINT_MAX_NDIM] = {};
+    long long stride = 1;
+    split_cols(h, h->d_pt, &stride, cols);
+    uint8_t* d_status = (uint8_t*)h->d_res + 8;
+    int rc = launch(h, cols, stride, 1, h->d_res, d_status, nullptr, 0, st);
+    if (rc != NINT_OK) return rc;
+    unsigned char res[16];
+    NINT_CUDA(cudaMemcpyAsync(res, h->d_res, 16, cudaMemcpyDeviceToHost, st));
+    NINT_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(out, res, es);
+    if (res[8] == NINT_STATUS_EXTRAPOLATE_ERROR)
+        return fail(NINT_E_EXTRAPOLATE, -1, "attempted to interpolate at point beyond grid data");
+    if (res[8] == NINT_STATUS_PANIC)
+        return fail(NINT_E_PANIC, -1, "the reference implementation would panic on this point");
+    return NINT_OK;
+}
+
+int nint_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(NINT_E_INVALID_ARGUMENT, -1, "ptr is NULL");
+    NINT_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable));
+    return NINT_OK;
+}
+
+int nint_host_free(void* ptr) {
+    NINT_CUDA(cudaFreeHost(ptr));
+    return NINT_OK;
+}
+
+const char* nint_last_error_message(void) { return t_err_msg.c_str(); }
+int nint_last_error_dim(void) { return t_err_dim; }
+const char* nint_version(void) { return "ninterp_b200 0.1.0 (semantics of ninterp 0.8.1)"; }
+uint64_t nint_launch_count(void) { return nint::g_launch_count.load(std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -1,0 +1,39 @@
+// nint_launch.cuh — launch helper shared by the instantiation units.
+#pragma once
+#include <atomic>
+
+#include "nint_device.cuh"
+
+namespace nint {
+
+extern std::atomic<unsigned long long> g_launch_count;
+
+template <class T, int N, bool IS_ND, int STRAT, int EXTRAP, bool SMEM>
+cudaError_t launch_one(const Params<T>& P, const LaunchCfg& cfg) {
+    auto kern = interp_kernel<T, N, IS_ND, STRAT, EXTRAP, SMEM>;
+    const unsigned smem = SMEM ? cfg.smem_bytes : 0u;
+    if (smem > 48u * 1024u) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    // resident CTAs per SM for this kernel at this shared-memory size (cached; homogeneous GPUs)
+    static unsigned cached_smem = ~0u;
+    static int cached_bps = 0;
+    int bps = cached_bps;
+    if (cached_smem != smem || bps == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kBlock, smem);
+        if (e != cudaSuccess) return e;
+        if (bps < 1) bps = 1;
+        cached_bps = bps;
+        cached_smem = smem;
+    }
+    const unsigned long long want = (P.n + kBlock - 1) / kBlock;
+    const unsigned long long cap = (unsigned long long)cfg.sm_count * (unsigned long long)bps;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (grid == 0) return cudaSuccess;
+    kern<<<grid, kBlock, smem, (cudaStream_t)cfg.stream>>>(P);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+}  // namespace nint

@@ -1,0 +1,202 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle: bit-exact values and statuses.
+
+Bar (BASELINE.json north_star): bit-exact for Nearest/LeftNearest/RightNearest; <=4 ulp (f64) /
+<=2 ulp (f32) for Linear.  The kernels execute the reference's operation sequence without FMA
+contraction, so Linear is held to bit-exact here as well (0 ulp).
+"""
+import numpy as np
+import pytest
+
+import oracle_binding as O
+
+pytestmark = pytest.mark.gpu
+
+LIN, NEA, LEFT, RIGHT = 0, 1, 2, 3
+ENABLE, FILL, CLAMP, WRAP, ERROR = 0, 1, 2, 3, 4
+FIXED, ND = 0, 1
+
+
+def _axes(rng, lens, dtype, mode="nonuniform"):
+    axes = []
+    for L in lens:
+        if mode == "uniform":
+            g = (np.arange(L) * 0.37 - 1.3).astype(dtype)
+        elif mode == "log":
+            g = np.sort(np.unique(np.logspace(-6, 3, L).astype(dtype)))
+            if len(g) < L:
+                g = np.concatenate([g, g[-1] + 1 + np.arange(L - len(g))]).astype(dtype)
+        elif mode == "dup":
+            g = np.cumsum(rng.uniform(0.5, 1.5, L)).astype(dtype)
+            if L >= 4:
+                g[L // 2] = g[L // 2 - 1]
+                g[-1] = g[-2]
+                g[1] = g[0]
+        elif mode == "offset":  # huge offset, tiny span: bucket edges are below one ulp of the nodes
+            base = dtype(1e15 if dtype == np.float64 else 1e7)
+            g = np.unique((base + np.cumsum(rng.uniform(1, 3, L))).astype(dtype))
+            while len(g) < L:
+                g = np.append(g, np.nextafter(g[-1], dtype(np.inf)) + dtype(4))
+            g = g[:L].astype(dtype)
+        elif mode == "wide":  # spans the whole finite range: the bucket width overflows
+            g = np.sort(np.concatenate([[-np.finfo(dtype).max], rng.uniform(-1e3, 1e3, L - 2), [np.finfo(dtype).max]])).astype(dtype)
+        else:
+            g = (np.cumsum(rng.uniform(0.5, 1.5, L)) + rng.uniform(-3, 3)).astype(dtype)
+        axes.append(np.ascontiguousarray(g))
+    return axes
+
+
+def _queries(rng, axes, n, dtype, frac_special=0.25):
+    """Random queries over [-0.3 span, 1.3 span] mixed with nodes, neighbours of nodes, +-0, inf, NaN, denormals."""
+    cols = []
+    for g in axes:
+        lo, hi = float(g[0]), float(g[-1])
+        if not np.isfinite(hi - lo):
+            lo, hi = -2e3, 2e3
+        span = max(hi - lo, 1e-3)
+        c = rng.uniform(lo - 0.3 * span, hi + 0.3 * span, n).astype(dtype)
+        k = int(n * frac_special)
+        pick = rng.integers(0, len(g), k)
+        kind = rng.integers(0, 9, k)
+        special = g[pick].astype(dtype)
+        special = np.where(kind == 1, np.nextafter(g[pick], dtype(np.inf)), special)
+        special = np.where(kind == 2, np.nextafter(g[pick], dtype(-np.inf)), special)
+        special = np.where(kind == 3, dtype(np.nan), special)
+        special = np.where(kind == 4, dtype(np.inf) * rng.choice([-1, 1], k).astype(dtype), special)
+        special = np.where(kind == 5, dtype(0.0) * rng.choice([-1, 1], k).astype(dtype), special)
+        special = np.where(kind == 6, np.finfo(dtype).tiny * dtype(0.5), special)
+        special = np.where(kind == 7, np.finfo(dtype).max * rng.choice([-1, 1], k).astype(dtype), special)
+        c[rng.permutation(n)[:k]] = special.astype(dtype)
+        cols.append(c)
+    return cols
+
+
+def _check(kind, lens, strategy, extrap, dtype, mode, n, seed, aos=False, frac_special=0.25):
+    from gpu_util import assert_same, expected_info, gpu_eval, make_pair
+
+    rng = np.random.default_rng(seed)
+    axes = _axes(rng, lens, dtype, mode)
+    values = rng.uniform(-1, 1, lens).astype(dtype)
+    g, o = make_pair(kind, axes, values, strategy, extrap, fill=-9.5, dtype=dtype)
+    cols = _queries(rng, axes, n, dtype, frac_special)
+    got, st, info = gpu_eval(g, cols, aos=aos)
+    want, st_want = o.eval(cols, nthreads=O.max_threads())
+    ctx = f"kind={kind} lens={lens} strat={strategy} extrap={extrap} {np.dtype(dtype).name} {mode}"
+    assert_same(got, st, want, st_want, ctx)
+    assert info == expected_info(st_want), ctx
+
+
+FIXED_CASES = [(FIXED, (33,)), (FIXED, (17, 9)), (FIXED, (9, 7, 11))]
+ND_CASES = [(ND, (13,)), (ND, (7, 5)), (ND, (5, 4, 6)), (ND, (4, 3, 4, 3)), (ND, (3, 4, 3, 2, 3)), (ND, (2, 3, 2, 3, 2, 2))]
+
+
+def _combos(cases):
+    out = []
+    for kind, lens in cases:
+        strategies = [LIN, NEA] + ([LEFT, RIGHT] if kind == FIXED and len(lens) == 1 else [])
+        for s in strategies:
+            for e in (ENABLE, FILL, CLAMP, WRAP, ERROR):
+                if e == ENABLE and s != LIN:
+                    continue
+                out.append((kind, lens, s, e))
+    return out
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("kind,lens,strategy,extrap", _combos(FIXED_CASES + ND_CASES))
+def test_all_policies_adversarial(kind, lens, strategy, extrap, dtype):
+    _check(kind, lens, strategy, extrap, dtype, "nonuniform", 20000, seed=hash((kind, lens, strategy, extrap)) % 2**31)
+
+
+@pytest.mark.parametrize("mode", ["uniform", "log", "dup", "offset", "wide"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_grid_shapes_stress_bracket(mode, dtype):
+    # the bucket table must never change the index the reference's binary search would return
+    for kind, lens, strategy in [(FIXED, (200,), LIN), (FIXED, (200,), LEFT), (FIXED, (64, 48), NEA), (FIXED, (20, 30, 25), LIN),
+                                 (ND, (12, 10, 9, 8), LIN)]:
+        for extrap in (ENABLE, CLAMP, WRAP, ERROR):
+            if extrap == ENABLE and strategy != LIN:
+                continue
+            _check(kind, lens, strategy, extrap, dtype, mode, 30000, seed=11)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_length_one_and_two_axes(dtype):
+    for kind, lens in [(FIXED, (1,)), (FIXED, (2,)), (FIXED, (1, 5)), (FIXED, (4, 1, 3)), (ND, (1,)), (ND, (1, 4)), (ND, (3, 1, 2)),
+                       (ND, (1, 1)), (ND, (2, 2, 1, 2))]:
+        strategies = [LIN, NEA] + ([LEFT, RIGHT] if kind == FIXED and len(lens) == 1 else [])
+        for s in strategies:
+            for e in (FILL, CLAMP, WRAP, ERROR) + ((ENABLE,) if s == LIN and min(lens) >= 2 else ()):
+                _check(kind, lens, s, e, dtype, "nonuniform", 4000, seed=5, frac_special=0.5)
+
+
+def test_aos_points_equal_soa_columns():
+    for kind, lens, s in [(FIXED, (40,), LIN), (FIXED, (12, 9), LIN), (FIXED, (9, 8, 7), LIN), (ND, (4, 5, 3, 4, 3), NEA)]:
+        _check(kind, lens, s, CLAMP, np.float64, "nonuniform", 50000, seed=3, aos=True)
+        _check(kind, lens, s, ERROR, np.float32, "nonuniform", 50000, seed=4, aos=True)
+
+
+def test_axes_too_large_for_shared_memory():
+    # 60k nodes * 8 B * 2 axes > the shared-memory budget: the global-memory variant must agree as well
+    _check(FIXED, (60000,), LIN, ERROR, np.float64, "nonuniform", 200000, seed=8, frac_special=0.05)
+    _check(FIXED, (60000,), RIGHT, WRAP, np.float64, "nonuniform", 200000, seed=8, frac_special=0.05)
+    _check(FIXED, (30000, 20), LIN, ENABLE, np.float64, "nonuniform", 200000, seed=9, frac_special=0.05)
+    _check(ND, (30000, 8), NEA, CLAMP, np.float64, "nonuniform", 200000, seed=10, frac_special=0.05)
+
+
+def test_strided_value_views():
+    # "view data": InterpData::view (data.rs:92-97) — non-contiguous values are honoured at upload
+    import ninterp_b200 as nb
+    from gpu_util import assert_same, gpu_eval
+
+    rng = np.random.default_rng(12)
+    big = rng.uniform(-1, 1, (14, 18, 10))
+    view = big[::2, 1::3, ::-1]                  # strides (2, 3, -1) elements
+    view_t = np.transpose(big, (2, 0, 1))[2:9]   # permuted axes
+    for v in (view, view_t):
+        axes = [np.cumsum(rng.uniform(0.5, 1.5, L)) for L in v.shape]
+        g = nb.Interp3D(*axes, v, nb.strategy.Linear, nb.Extrapolate.Clamp)
+        o = O.Oracle(axes, np.ascontiguousarray(v), LIN, CLAMP)
+        cols = _queries(rng, axes, 20000, np.float64, 0.1)
+        got, st, _ = gpu_eval(g, cols)
+        want, st_want = o.eval(cols)
+        assert_same(got, st, want, st_want, "strided view")
+
+
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+def test_host_pipeline_multi_chunk(layout):
+    # nint_interpolate_batch_host: > 2 chunks of 4 Mi points, status + info, ragged last chunk
+    import ninterp_b200 as nb
+
+    rng = np.random.default_rng(21)
+    axes = [np.cumsum(rng.uniform(0.5, 1.5, L)) for L in (50, 40, 30)]
+    values = rng.uniform(-1, 1, (50, 40, 30))
+    g = nb.Interp3D(*axes, values, nb.strategy.Linear, nb.Extrapolate.Error)
+    o = O.Oracle(axes, values, LIN, ERROR)
+    n = (4 << 20) * 2 + 12345
+    cols = [rng.uniform(a[0], a[-1], n) for a in axes]
+    bad = rng.permutation(n)[:1000]
+    cols[1][bad] = axes[1][-1] + 1.0
+    cols[2][bad[:10]] = np.nan
+    pts = cols if layout == "soa" else np.stack(cols, axis=1)
+    got, st, info = g.interpolate_batch_host(pts, return_status=True)
+    want, st_want = o.eval(cols, nthreads=O.max_threads())
+    from gpu_util import assert_same, expected_info
+
+    assert_same(got, st, want, st_want, "host pipeline")
+    assert info == expected_info(st_want)
+    with pytest.raises(nb.InterpolateError):
+        g.interpolate_batch_host(pts)
+    # a clean batch returns values only
+    ok = [rng.uniform(a[0], a[-1], 100000) for a in axes]
+    vals = g.interpolate_batch_host(ok if layout == "soa" else np.stack(ok, axis=1))
+    assert_same(vals, np.zeros(100000, np.uint8), *o.eval(ok), "host pipeline clean")
+
+
+def test_empty_batch():
+    import ninterp_b200 as nb
+    import torch
+
+    g = nb.Interp2D([0., 1.], [0., 1.], [[0., 1.], [2., 3.]])
+    out = g.interpolate_batch([torch.empty(0, dtype=torch.float64, device="cuda")] * 2)
+    assert out.numel() == 0
+    assert g.interpolate_batch_host(np.empty((0, 2))).size == 0
