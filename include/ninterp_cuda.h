@@ -166,6 +166,12 @@ NINT_API int nint_host_free(void* ptr);
 NINT_API const char* nint_last_error_message(void);
 NINT_API int nint_last_error_dim(void);
 
+/* Device self-test: n pseudo-random and adversarial (a, w) pairs, counting where the kernels'
+ * FMA-corrected reciprocal division differs from IEEE `a / w` (must be 0), and how many pairs
+ * took the fast path. */
+NINT_API int nint_selftest_divide(int dtype, uint64_t n, uint64_t seed, uint64_t* mismatches,
+                                  uint64_t* fast_path_taken);
+
 /* Library version, and the number of kernel launches issued by this process (bench accounting). */
 NINT_API const char* nint_version(void);
 NINT_API uint64_t nint_launch_count(void);

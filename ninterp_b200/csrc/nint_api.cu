@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -79,7 +80,7 @@ const char* extrap_name(int e) {
 
 struct AxisMeta {
     int L = 0, M = 0;
-    unsigned node_off = 0, lut_off = 0;
+    unsigned node_off = 0, lut_off = 0, rcp_off = 0;
     double g0 = 0, gl = 0, inv_w = 0;
     long long vstride = 0;
 };
@@ -115,6 +116,7 @@ struct nint_handle {
     unsigned char* d_pack = nullptr;
     unsigned pack_bytes = 0;
     bool smem_axes = true;
+    float l2_frac = 0.0f;  // share of the value table held evict_last in L2
     AxisMeta ax[NINT_MAX_NDIM];
     int sm_count = 0;
     // scratch for the synchronous entry points
@@ -211,7 +213,7 @@ int build_pack(nint_handle* h) {
         for (int d = 0; d < n; ++d) {
             const unsigned long long L = h->axis_len[d];
             unsigned long long M = std::max<unsigned long long>(1, (unsigned long long)(per_cell * (double)L));
-            t += align_up((unsigned)(L * es), 16) + M * 8ull;
+            t += align_up((unsigned)((L + 2) * es), 16) + align_up((unsigned)(L * es), 16) + align_up((unsigned)(M * 8ull), 16);
         }
         return t;
     };
@@ -247,12 +249,38 @@ int build_pack(nint_handle* h) {
         a.inv_w = inv_w;
         std::vector<uint2> lut;
         build_lut(h->dtype, nodes, L, M, a.g0, inv_w, lut);
+        // nodes, followed by two +inf pads (count_less may look one and two nodes past its upper bound)
         a.node_off = (unsigned)pack.size();
-        pack.resize(pack.size() + align_up((unsigned)(L * es), 16), 0);
+        pack.resize(pack.size() + align_up((unsigned)((L + 2) * es), 16), 0);
         std::memcpy(pack.data() + a.node_off, nodes, (size_t)L * es);
+        for (int k = 0; k < 2; ++k) {
+            if (h->dtype == NINT_F64) {
+                const double inf = std::numeric_limits<double>::infinity();
+                std::memcpy(pack.data() + a.node_off + (size_t)(L + k) * es, &inf, es);
+            } else {
+                const float inf = std::numeric_limits<float>::infinity();
+                std::memcpy(pack.data() + a.node_off + (size_t)(L + k) * es, &inf, es);
+            }
+        }
         a.lut_off = (unsigned)pack.size();
         pack.resize(pack.size() + align_up((unsigned)(M * 8), 16), 0);
         std::memcpy(pack.data() + a.lut_off, lut.data(), (size_t)M * 8);
+        // per-cell reciprocals for div_cell(): only cells whose width is comfortably normal
+        a.rcp_off = (unsigned)pack.size();
+        pack.resize(pack.size() + align_up((unsigned)(L * es), 16), 0);
+        for (int l = 0; l + 1 < L; ++l) {
+            if (h->dtype == NINT_F64) {
+                const double w = ((const double*)nodes)[l + 1] - ((const double*)nodes)[l];
+                double r = 0.0;
+                if (w >= 0x1p-500 && w < 0x1p500) r = 1.0 / w;
+                std::memcpy(pack.data() + a.rcp_off + (size_t)l * es, &r, es);
+            } else {
+                const float w = ((const float*)nodes)[l + 1] - ((const float*)nodes)[l];
+                float r = 0.0f;
+                if (w >= 0x1p-60f && w < 0x1p60f) r = 1.0f / w;
+                std::memcpy(pack.data() + a.rcp_off + (size_t)l * es, &r, es);
+            }
+        }
     }
     h->pack_bytes = (unsigned)pack.size();
     if (h->pack_bytes == 0) return NINT_OK;
@@ -274,7 +302,9 @@ int upload_values(nint_handle* h, const void* values_host, const ptrdiff_t* stri
             expect *= (ptrdiff_t)h->value_shape[d];
         }
     }
-    NINT_CUDA(cudaMalloc(&h->d_values, std::max<size_t>(h->values_len, 1) * es));
+    // one aligned pair of slack: ld_pair() may fetch the pair after the last element
+    NINT_CUDA(cudaMalloc(&h->d_values, (std::max<size_t>(h->values_len, 1) + 4) * es));
+    NINT_CUDA(cudaMemset((unsigned char*)h->d_values + std::max<size_t>(h->values_len, 1) * es, 0, 4 * es));
     if (dense) {
         NINT_CUDA(cudaMemcpy(h->d_values, values_host, h->values_len * es, cudaMemcpyHostToDevice));
         return NINT_OK;
@@ -305,12 +335,14 @@ void fill_params(const nint_handle* h, nint::Params<T>& P) {
     P.pack_bytes = h->pack_bytes;
     P.fill = (T)h->fill;
     P.extrap = h->extrap;
+    P.l2_frac = h->l2_frac;
     for (int d = 0; d < h->ndim_eff; ++d) {
         const AxisMeta& a = h->ax[d];
         P.L[d] = a.L;
         P.M[d] = a.M;
         P.node_off[d] = a.node_off;
         P.lut_off[d] = a.lut_off;
+        P.rcp_off[d] = a.rcp_off;
         P.vstride[d] = a.vstride;
         P.g0[d] = (T)a.g0;
         P.gl[d] = (T)a.gl;
@@ -498,6 +530,13 @@ int nint_create(int device, int kind, int dtype, int ngrid, const size_t* axis_l
         return cuda_fail(e, "cudaGetDeviceProperties");
     }
     h->sm_count = prop.multiProcessorCount;
+    {
+        // Tables that fit keep all their lines evict_last; larger ones keep a stable subset
+        const double table_bytes = (double)h->values_len * (double)es;
+        double frac = table_bytes > 0 ? std::min(1.0, 0.75 * (double)prop.l2CacheSize / table_bytes) : 1.0;
+        if (const char* env = std::getenv("NINT_L2_FRAC")) frac = std::atof(env);
+        h->l2_frac = (float)std::max(0.0, std::min(1.0, frac));
+    }
     rc = upload_values(h, values_host, value_strides);
     if (rc == NINT_OK && !h->constant) rc = build_pack(h);
     if (rc == NINT_OK) {

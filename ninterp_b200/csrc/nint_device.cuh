@@ -40,18 +40,21 @@ struct Params {
     unsigned long long index_base;  // batch index of point 0 (host pipeline chunks)
     T fill;
     int extrap;  // policy when the kernel is instantiated with EXTRAP == kExtrapRuntime
+    float l2_frac;  // fraction of the value table kept evict_last in L2 (0 = no hint)
     int L[kMaxDim];
     int M[kMaxDim];
     unsigned node_off[kMaxDim];  // byte offsets into the pack
     unsigned lut_off[kMaxDim];
+    unsigned rcp_off[kMaxDim];   // per cell l: RN(1 / (g[l+1] - g[l])), or 0 when outside the safe window
     long long vstride[kMaxDim];  // element strides of `values`
     T g0[kMaxDim], gl[kMaxDim], inv_w[kMaxDim];
 };
 
 template <class T>
 struct AxisRef {
-    const T* g;        // nodes
+    const T* g;        // L nodes followed by two +inf pads
     const uint2* lut;  // bucket b -> [lo, hi]: the node count below any point of the bucket
+    const T* rcp;      // rcp[l] = RN(1 / (g[l+1] - g[l])) for cells inside the safe exponent window, else 0
     int L, M;
     T g0, gl, inv_w;
 };
@@ -72,8 +75,51 @@ template <class T>
 __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
 template <class T>
 __device__ __forceinline__ void st_stream(T* p, T v) { __stcs(p, v); }
+
+// Value-table loads carry an L2 cache policy: a fraction of the table's lines is held evict_last,
+// the rest evict_first, so that a table larger than L2 keeps a stable resident subset instead of
+// thrashing one 32-byte sector per 128-byte line ("L2 residency").
+__device__ __forceinline__ unsigned long long make_table_policy(float frac) {
+    unsigned long long pol;
+    if (frac > 0.0f) {
+        asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol) : "f"(frac));
+    } else {
+        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    }
+    return pol;
+}
+__device__ __forceinline__ double ld_table(const double* p, unsigned long long pol) {
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ld_table(const float* p, unsigned long long pol) {
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void ld_table2(const double* p, unsigned long long pol, double& a, double& b) {
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(a), "=d"(b) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void ld_table2(const float* p, unsigned long long pol, float& a, float& b) {
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(a), "=f"(b) : "l"(p), "l"(pol));
+}
+
+// Two adjacent table elements row[0], row[1] with one aligned vector load; when `row` sits in the upper
+// half of its aligned pair a second (predicated) vector load fetches the neighbour.  The table is
+// allocated with one pair of slack so the neighbour load never leaves the allocation.
 template <class T>
-__device__ __forceinline__ T ld_table(const T* p) { return __ldg(p); }
+__device__ __forceinline__ void ld_pair(const T* row, unsigned long long pol, T& lo, T& hi) {
+    const unsigned long long addr = (unsigned long long)row;
+    const bool odd = (addr & sizeof(T)) != 0;
+    const T* base = (const T*)(addr & ~(unsigned long long)(2 * sizeof(T) - 1));
+    T a0, a1, b0 = T(0), b1 = T(0);
+    ld_table2(base, pol, a0, a1);
+    if (odd) ld_table2(base + 2, pol, b0, b1);
+    lo = odd ? a1 : a0;
+    hi = odd ? b0 : a1;
+    (void)b1;
+}
 
 // c = #{ i : g[i] < p } for a non-NaN p.  The bucket table bounds c to a handful of candidates
 // (one bucket of slack on each side absorbs the rounding of the bucket index); the decision is
@@ -85,6 +131,12 @@ __device__ __forceinline__ int count_less(const AxisRef<T>& a, T p) {
     const uint2 e = a.lut[b];
     int lo = (int)e.x;
     int n = (int)e.y - (int)e.x;
+    if (n <= 2) {
+        // nodes at or beyond the upper bound are >= p and the two pads are +inf: count two unconditionally
+        const T n0 = a.g[lo];
+        const T n1 = a.g[lo + 1];
+        return lo + (n0 < p ? 1 : 0) + (n1 < p ? 1 : 0);
+    }
     while (n > 0) {
         const int half = n >> 1;
         const bool lt = a.g[lo + half] < p;
@@ -92,6 +144,35 @@ __device__ __forceinline__ int count_less(const AxisRef<T>& a, T p) {
         n = lt ? n - half - 1 : half;
     }
     return lo;
+}
+
+// a / w, correctly rounded, for a cell whose reciprocal r = RN(1/w) was prepared on the host.
+// q0 = RN(a*r) is within 2 ulp of a/w; one FMA residual step makes it faithful and a second one
+// (Markstein's theorem, r being the correctly rounded reciprocal) makes it the correctly rounded
+// quotient, i.e. bit-identical to the IEEE division the reference performs.  The exponent window
+// (|a|, w in [2^-500, 2^500) for f64, [2^-60, 2^60) for f32) keeps every intermediate normal; anything
+// else (zero, subnormal, huge, inf, NaN, or r == 0 from the host) takes the hardware division.
+__device__ __forceinline__ double div_cell(double a, double w, double r) {
+    const unsigned hi = (unsigned)__double2hiint(a) & 0x7fffffffu;
+    if ((hi - 0x20b00000u) < 0x3e800000u && r != 0.0) {
+        double q = a * r;
+        double e = __fma_rn(-q, w, a);
+        q = __fma_rn(e, r, q);
+        e = __fma_rn(-q, w, a);
+        return __fma_rn(e, r, q);
+    }
+    return a / w;
+}
+__device__ __forceinline__ float div_cell(float a, float w, float r) {
+    const unsigned bits = (unsigned)__float_as_int(a) & 0x7fffffffu;
+    if ((bits - 0x21800000u) < 0x3c000000u && r != 0.0f) {
+        float q = a * r;
+        float e = __fmaf_rn(-q, w, a);
+        q = __fmaf_rn(e, r, q);
+        e = __fmaf_rn(-q, w, a);
+        return __fmaf_rn(e, r, q);
+    }
+    return a / w;
 }
 
 // lib.rs:81-83 with Rust's float rem_euclid (fmod, then `+ |b|` when negative)
@@ -119,9 +200,10 @@ __device__ __forceinline__ T clamp_coord(T x, T lo, T hi) {
 // LEN1      InterpND returns early when a single element is left after collapsing
 //           (n/strategies.rs:47-50), which also covers un-collapsed axes of length 1.
 // ---------------------------------------------------------------------------------------------
-template <class T, int N, bool COLLAPSE, bool LEN1>
+template <class T, int N, bool COLLAPSE, bool LEN1, bool INRANGE>
 __device__ __forceinline__ T eval_linear(const AxisRef<T> (&ax)[N], const long long (&vs)[N],
-                                         const T* __restrict__ values, const T (&q)[N], unsigned& status) {
+                                         const T* __restrict__ values, unsigned long long pol, const T (&q)[N],
+                                         unsigned& status) {
     int idx[N];
     T t[N];
     bool fixed[N];
@@ -130,7 +212,8 @@ __device__ __forceinline__ T eval_linear(const AxisRef<T> (&ax)[N], const long l
 #pragma unroll
     for (int d = 0; d < N; ++d) {
         const T p = q[d];
-        const bool isnan = (p != p);
+        // INRANGE: the front-end already established g0 <= p <= gl, so p is not NaN
+        const bool isnan = INRANGE ? false : (p != p);
         const int L = ax[d].L;
         const int c = isnan ? 0 : count_less(ax[d], p);
         bool hit = false;
@@ -149,28 +232,38 @@ __device__ __forceinline__ T eval_linear(const AxisRef<T> (&ax)[N], const long l
                 const T gl_ = ax[d].g[l];
                 const T gu_ = ax[d].g[l + 1];
                 idx[d] = l;
-                t[d] = (p - gl_) / (gu_ - gl_);
+                t[d] = div_cell(p - gl_, gu_ - gl_, ax[d].rcp[l]);
             }
         }
     }
     long long base = 0;
 #pragma unroll
     for (int d = 0; d < N; ++d) base += (long long)idx[d] * vs[d];
-    if (LEN1 && single) return ld_table(values + base);
+    if (LEN1 && single) return ld_table(values + base, pol);
     if (panic) {
         status = NINT_STATUS_PANIC;
         return T(0);
     }
-    // gather the cell: corner bit of axis 0 is the most significant one
+    // Gather the cell as 2^(N-1) rows of two elements adjacent along the last axis (stride 1).
+    // Row r: bit (N-2-d) of r selects the upper node of axis d, so axis 0 is the most significant bit.
+    constexpr int kRows = 1 << (N - 1);
+    const T* rowp[kRows];
+    rowp[0] = values + base;
+#pragma unroll
+    for (int r = 1; r < kRows; ++r) {
+        const int low = r & (-r);          // lowest set bit
+        int d = 0;
+#pragma unroll
+        for (int k = 0; k < N - 1; ++k) if ((low >> (N - 2 - k)) & 1) d = k;
+        rowp[r] = rowp[r & (r - 1)] + (fixed[d] ? 0 : vs[d]);
+    }
     T cube[1 << N];
 #pragma unroll
-    for (int c = 0; c < (1 << N); ++c) {
-        long long off = base;
-#pragma unroll
-        for (int d = 0; d < N; ++d) {
-            if ((c >> (N - 1 - d)) & 1) off += fixed[d] ? 0 : vs[d];
-        }
-        cube[c] = ld_table(values + off);
+    for (int r = 0; r < kRows; ++r) {
+        T lo, hi;
+        ld_pair(rowp[r], pol, lo, hi);
+        cube[2 * r] = lo;
+        cube[2 * r + 1] = fixed[N - 1] ? lo : hi;
     }
     // reduce axis 0 first, then 1, ...: v_l * (1 - t) + v_u * t, each op rounded separately
 #pragma unroll
@@ -190,7 +283,8 @@ __device__ __forceinline__ T eval_linear(const AxisRef<T> (&ax)[N], const long l
 // NEAREST (N-D and hard-coded) and, for N == 1, LEFT_NEAREST / RIGHT_NEAREST
 template <class T, int N, bool COLLAPSE, bool LEN1, int STRAT>
 __device__ __forceinline__ T eval_index(const AxisRef<T> (&ax)[N], const long long (&vs)[N],
-                                        const T* __restrict__ values, const T (&q)[N], unsigned& status) {
+                                        const T* __restrict__ values, unsigned long long pol, const T (&q)[N],
+                                        unsigned& status) {
     int idx[N];
     bool panic = false;
     bool single = true;
@@ -230,12 +324,12 @@ __device__ __forceinline__ T eval_index(const AxisRef<T> (&ax)[N], const long lo
     long long off = 0;
 #pragma unroll
     for (int d = 0; d < N; ++d) off += (long long)idx[d] * vs[d];
-    if (LEN1 && single) return ld_table(values + off);  // un-collapsed length-1 axes sit at index 0
+    if (LEN1 && single) return ld_table(values + off, pol);  // un-collapsed length-1 axes sit at index 0
     if (panic) {
         status = NINT_STATUS_PANIC;
         return T(0);
     }
-    return ld_table(values + off);
+    return ld_table(values + off, pol);
 }
 
 __device__ __forceinline__ unsigned long long shfl_down_u64(unsigned long long v, int delta) {
@@ -265,6 +359,7 @@ __global__ void __launch_bounds__(kBlock) interp_kernel(const __grid_constant__ 
     for (int d = 0; d < N; ++d) {
         ax[d].g = reinterpret_cast<const T*>(pack + P.node_off[d]);
         ax[d].lut = reinterpret_cast<const uint2*>(pack + P.lut_off[d]);
+        ax[d].rcp = reinterpret_cast<const T*>(pack + P.rcp_off[d]);
         ax[d].L = P.L[d];
         ax[d].M = P.M[d];
         ax[d].g0 = P.g0[d];
@@ -275,6 +370,9 @@ __global__ void __launch_bounds__(kBlock) interp_kernel(const __grid_constant__ 
     const int extrap = (EXTRAP == kExtrapRuntime) ? P.extrap : EXTRAP;
     constexpr bool kCollapse = IS_ND || (N == 1);
     constexpr bool kLen1 = IS_ND;
+    // under Error and Fill only in-range (hence non-NaN) points reach the strategy
+    constexpr bool kInRange = (EXTRAP == NINT_EXTRAPOLATE_ERROR) || (EXTRAP == NINT_EXTRAPOLATE_FILL);
+    const unsigned long long pol = make_table_policy(P.l2_frac);
 
     unsigned long long n_err = 0, n_panic = 0;
     unsigned long long first_err = ~0ull, first_panic = ~0ull;
@@ -309,8 +407,8 @@ __global__ void __launch_bounds__(kBlock) interp_kernel(const __grid_constant__ 
             // Enable: evaluate as is (:203)
         }
         if (!done) {
-            if (STRAT == NINT_LINEAR) result = eval_linear<T, N, kCollapse, kLen1>(ax, vs, P.values, q, status);
-            else result = eval_index<T, N, kCollapse, kLen1, STRAT>(ax, vs, P.values, q, status);
+            if (STRAT == NINT_LINEAR) result = eval_linear<T, N, kCollapse, kLen1, kInRange>(ax, vs, P.values, pol, q, status);
+            else result = eval_index<T, N, kCollapse, kLen1, STRAT>(ax, vs, P.values, pol, q, status);
         }
         if (status != NINT_STATUS_OK) {
             result = quiet_nan<T>();

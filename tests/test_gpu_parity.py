@@ -121,12 +121,22 @@ def test_grid_shapes_stress_bracket(mode, dtype):
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
 def test_length_one_and_two_axes(dtype):
-    for kind, lens in [(FIXED, (1,)), (FIXED, (2,)), (FIXED, (1, 5)), (FIXED, (4, 1, 3)), (ND, (1,)), (ND, (1, 4)), (ND, (3, 1, 2)),
-                       (ND, (1, 1)), (ND, (2, 2, 1, 2))]:
+    for kind, lens in [(FIXED, (1,)), (FIXED, (2,)), (FIXED, (1, 5)), (FIXED, (4, 1, 3)), (ND, (1, 4)), (ND, (3, 1, 2)),
+                       (ND, (2, 2, 1, 2))]:
         strategies = [LIN, NEA] + ([LEFT, RIGHT] if kind == FIXED and len(lens) == 1 else [])
         for s in strategies:
             for e in (FILL, CLAMP, WRAP, ERROR) + ((ENABLE,) if s == LIN and min(lens) >= 2 else ()):
                 _check(kind, lens, s, e, dtype, "nonuniform", 4000, seed=5, frac_special=0.5)
+
+
+def test_nd_single_value_needs_empty_grid():
+    # n/mod.rs:71-83, n/tests.rs:370-381: an InterpND over one value is 0-D and rejects a non-empty grid
+    import ninterp_b200 as nb
+
+    for grid, vals in (([[1.0]], [0.0]), ([[1.0], [2.0]], [[0.0]])):
+        with pytest.raises(nb.ValidateError) as e:
+            nb.InterpND(grid, vals)
+        assert e.value.variant == "Other"
 
 
 def test_aos_points_equal_soa_columns():
@@ -200,3 +210,19 @@ def test_empty_batch():
     out = g.interpolate_batch([torch.empty(0, dtype=torch.float64, device="cuda")] * 2)
     assert out.numel() == 0
     assert g.interpolate_batch_host(np.empty((0, 2))).size == 0
+
+
+@pytest.mark.parametrize("dtype_code,name", [(1, "f64"), (0, "f32")])
+def test_division_fast_path_is_ieee_exact(dtype_code, name):
+    # div_cell(): q = a*r corrected by two FMA residual steps must equal IEEE a / w bit-for-bit
+    import ctypes as C
+
+    from ninterp_b200 import _lib
+
+    lib = _lib.lib()
+    bad, fast = C.c_uint64(), C.c_uint64()
+    n = 2_000_000_000
+    for seed in (1, 2):
+        assert lib.nint_selftest_divide(dtype_code, n, seed, C.byref(bad), C.byref(fast)) == 0
+        assert bad.value == 0, f"{name}: {bad.value} of {n} quotients differ from IEEE division"
+        assert fast.value > n // 4, f"{name}: fast path barely exercised ({fast.value})"

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Small driver for ncu captures: builds one BASELINE workload at reduced size and launches it a few times.
+
+usage: python tools/prof_case.py --case random|sorted|nonuniform|nd5|2d|1d --points 1e8 --launches 3
+Prints the CUDA-event time per launch (never quote a number printed under ncu).
+"""
+import argparse
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+import ninterp_b200 as nb  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", default="random")
+    ap.add_argument("--points", type=float, default=1e8)
+    ap.add_argument("--launches", type=int, default=3)
+    ap.add_argument("--status", action="store_true")
+    a = ap.parse_args()
+    n = int(a.points)
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(0)
+    if a.case in ("random", "sorted", "nonuniform"):
+        axes, values = bench.grid_and_values(uniform=a.case != "nonuniform")
+        g = nb.Interp3D(*axes, values, nb.strategy.Linear, nb.Extrapolate.Error)
+        cols = bench.gen_random(torch, n, dev, seed=1)
+        if a.case == "sorted":
+            bench.fill_cell_sorted(torch, cols, dev, seed=2)
+        tdt = torch.float64
+    elif a.case == "nd5":
+        axes = [np.cumsum(rng.uniform(0.5, 1.5, 32)).astype(np.float32) for _ in range(5)]
+        values = rng.uniform(0, 1, (32,) * 5).astype(np.float32)
+        g = nb.InterpND(axes, values, nb.strategy.Linear, nb.Extrapolate.Wrap, dtype=np.float32)
+        cols = [(torch.rand(n, dtype=torch.float32, device=dev) * 1.5 - 0.25) * float(ax[-1] - ax[0]) + float(ax[0]) for ax in axes]
+        tdt = torch.float32
+    elif a.case == "2d":
+        axes = [np.arange(2048.0)] * 2
+        values = rng.uniform(0, 1, (2048, 2048))
+        g = nb.Interp2D(*axes, values, nb.strategy.Linear, nb.Extrapolate.Clamp)
+        cols = [torch.rand(n, dtype=torch.float64, device=dev) * 2047 * 1.1 - 0.05 * 2047 for _ in range(2)]
+        tdt = torch.float64
+    else:
+        gx = np.concatenate([[0.0], np.cumsum(rng.uniform(0.5, 1.5, 999))])
+        g = nb.Interp1D(gx, rng.uniform(0, 1, 1000), nb.strategy.Linear, nb.Extrapolate.Error)
+        cols = [torch.rand(n, dtype=torch.float64, device=dev) * gx[-1]]
+        tdt = torch.float64
+    out = torch.empty(n, dtype=tdt, device=dev)
+    status = torch.empty(n, dtype=torch.uint8, device=dev) if a.status else None
+    torch.cuda.synchronize()
+    for k in range(a.launches):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.interpolate_batch(cols, out=out, status=status)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        print(f"{a.case} launch {k}: {ms:.3f} ms  {n / ms / 1e6:.2f} Gpt/s", flush=True)
+
+
+if __name__ == "__main__":
+    main()
