@@ -46,7 +46,7 @@ def parse_args():
     return ap.parse_args()
 
 
-def grid_and_values(seed=1234567890, uniform=True):
+def grid_and_values(seed=1234567890, uniform=True, GRID=GRID):
     rng = np.random.default_rng(seed)  # benches/benchmark.rs:13 seed
     if uniform:
         axes = [np.arange(GRID, dtype=np.float64) * (1.0 / (GRID - 1)) for _ in range(3)]
@@ -193,7 +193,7 @@ def gen_random(torch, n, dev, seed, chunk=1 << 27):
     return cols
 
 
-def fill_cell_sorted(torch, cols, dev, seed, chunk=1 << 26):
+def fill_cell_sorted(torch, cols, dev, seed, chunk=1 << 26, GRID=GRID):
     """Overwrites cols with queries visited in grid-cell order (what a pre-binned caller provides)."""
     n = cols[0].numel()
     ncell = (GRID - 1) ** 3

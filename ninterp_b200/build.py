@@ -42,6 +42,7 @@ def _stamp() -> str:
                                                                       Path(__file__)]):
         h.update(f.name.encode())
         h.update(f.read_bytes())
+    h.update(os.environ.get("NINT_NVCC_EXTRA", "").encode())
     return h.hexdigest()
 
 
@@ -52,10 +53,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return SO
     nvcc = _nvcc()
     OBJ.mkdir(exist_ok=True)
+    extra = os.environ.get("NINT_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DNINT_MIN_CTAS=3
 
     def compile_one(src: str):
         obj = OBJ / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         (OBJ / (src + ".log")).write_text(r.stdout + r.stderr)
         if r.returncode != 0:

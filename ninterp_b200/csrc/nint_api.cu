@@ -80,9 +80,11 @@ const char* extrap_name(int e) {
 
 struct AxisMeta {
     int L = 0, M = 0;
-    unsigned node_off = 0, lut_off = 0, rcp_off = 0;
-    double g0 = 0, gl = 0, inv_w = 0;
+    unsigned node_off = 0, lut_off = 0;
+    double g0 = 0, gl = 0, inv_w = 0, inv_h = 0;
+    int flags = 0;
     long long vstride = 0;
+    long long cstride = 0;  // stride of this axis in the cell-packed table, in cells
 };
 
 // Device buffers of one in-flight chunk of the host pipeline.
@@ -113,6 +115,7 @@ struct nint_handle {
     double fill = 0.0;  // value of Fill(v), exact in T
     size_t values_len = 1;
     void* d_values = nullptr;
+    void* d_cells = nullptr;  // cell-packed copy of the table for Linear (2^N corners per cell), or NULL
     unsigned char* d_pack = nullptr;
     unsigned pack_bytes = 0;
     bool smem_axes = true;
@@ -204,83 +207,122 @@ void build_lut(int dtype, const void* nodes, int L, int M, double g0, double inv
 constexpr unsigned kSmemPreferred = 64u * 1024u;   // keeps several CTAs resident per SM
 constexpr unsigned kSmemLimit = 200u * 1024u;      // below the 227 KB opt-in ceiling
 
+// Axis classification for the fast path: strictly increasing nodes (>= 2) may use it; evenly spaced
+// ones get a direct cell guess (cells per unit length), verified on the device against the real nodes.
+void classify_axis(const nint_handle* h, int d, AxisMeta& a) {
+    const void* nodes = h->axes_host[d].data();
+    const int L = (int)h->axis_len[d];
+    a.L = L;
+    a.g0 = load_elem(h->dtype, nodes, 0);
+    a.gl = load_elem(h->dtype, nodes, L - 1);
+    bool strict = L >= 2;
+    for (int i = 0; i + 1 < L && strict; ++i) strict = load_elem(h->dtype, nodes, i) < load_elem(h->dtype, nodes, i + 1);
+    a.flags = strict ? nint::kAxisFast : 0;
+    a.inv_h = 0.0;
+    const double span = a.gl - a.g0;
+    if (strict && std::isfinite(span) && span > 0.0) {
+        const double hh = span / (double)(L - 1);
+        bool uniform = true;
+        for (int i = 0; i < L && uniform; ++i)
+            uniform = std::fabs((load_elem(h->dtype, nodes, i) - a.g0) - hh * (double)i) <= 1e-3 * hh;
+        double inv_h = (double)(L - 1) / span;
+        if (h->dtype == NINT_F32) inv_h = (double)(float)inv_h;
+        if (uniform && std::isfinite(inv_h) && inv_h > 0.0) {
+            a.flags |= nint::kAxisUniform;
+            a.inv_h = inv_h;
+        }
+    }
+}
+
+// Bucket table of axis d with `per_cell` buckets per cell.  Returns the share of buckets whose candidate
+// range is wider than the two nodes the fast path inspects.
+double make_buckets(const nint_handle* h, int d, double per_cell, AxisMeta& a, std::vector<uint2>& lut) {
+    const void* nodes = h->axes_host[d].data();
+    const int L = a.L;
+    int M = (int)std::min<double>(std::max(1.0, per_cell * (double)L), h->dtype == NINT_F64 ? 16777216.0 : 1048576.0);
+    double inv_w = 0.0;
+    const double span = a.gl - a.g0;
+    if (L >= 2 && M >= 2 && std::isfinite(span) && span > 0.0) {
+        inv_w = (double)M / span;
+        if (h->dtype == NINT_F32) inv_w = (double)(float)inv_w;  // the device multiplies by this in T
+        const double w = 1.0 / inv_w;
+        if (!std::isfinite(inv_w) || !(inv_w > 0.0) || !std::isfinite(w) || !(w > 0.0)) inv_w = 0.0;
+    }
+    if (inv_w == 0.0) M = 1;  // degenerate axis: one bucket, plain binary search over all nodes
+    a.M = M;
+    a.inv_w = inv_w;
+    build_lut(h->dtype, nodes, L, M, a.g0, inv_w, lut);
+    size_t wide = 0;
+    for (const uint2& e : lut) wide += (e.y - e.x > 2u) ? 1 : 0;
+    return (double)wide / (double)M;
+}
+
 int build_pack(nint_handle* h) {
     const int n = h->ndim_eff;
     const size_t es = elem_size(h->dtype);
-    // choose bucket counts: 2 per cell if it fits comfortably, fewer otherwise
-    auto total_bytes = [&](double per_cell) {
-        unsigned long long t = 0;
-        for (int d = 0; d < n; ++d) {
-            const unsigned long long L = h->axis_len[d];
-            unsigned long long M = std::max<unsigned long long>(1, (unsigned long long)(per_cell * (double)L));
-            t += align_up((unsigned)((L + 2) * es), 16) + align_up((unsigned)(L * es), 16) + align_up((unsigned)(M * 8ull), 16);
+    unsigned long long rec_bytes = 0;
+    for (int d = 0; d < n; ++d) {
+        classify_axis(h, d, h->ax[d]);
+        rec_bytes += align_up((unsigned)((h->axis_len[d] + 2) * 2 * es), 16);
+    }
+    h->smem_axes = rec_bytes + 16ull * n <= kSmemLimit;
+    // Bucket tables: uniform axes only need them on the general path (1 bucket per cell); the others
+    // refine until (almost) every bucket narrows the bracket to two nodes, within the memory budget.
+    const unsigned long long budget = h->smem_axes ? kSmemLimit : (64ull << 20);
+    const unsigned long long soft = h->smem_axes ? kSmemPreferred : (64ull << 20);
+    std::vector<std::vector<uint2>> luts(n);
+    unsigned long long lut_bytes = 0;
+    for (int d = 0; d < n; ++d) {
+        AxisMeta& a = h->ax[d];
+        const bool uniform = (a.flags & nint::kAxisUniform) != 0;
+        double per_cell = uniform ? 1.0 : 2.0;
+        // shrink first if even the starting table does not fit
+        while (per_cell > 1.0 / 64 && rec_bytes + lut_bytes + (unsigned long long)(per_cell * a.L) * 8 > budget) per_cell *= 0.5;
+        double wide = make_buckets(h, d, per_cell, a, luts[d]);
+        while (!uniform && wide > 0.002 && per_cell < 16.0) {
+            const unsigned long long next = rec_bytes + lut_bytes + (unsigned long long)(2 * per_cell * a.L) * 8;
+            if (next > soft) break;
+            per_cell *= 2.0;
+            wide = make_buckets(h, d, per_cell, a, luts[d]);
         }
-        return t;
-    };
-    double per_cell = 2.0;
-    unsigned long long nodes_only = total_bytes(0.0);
-    if (nodes_only > kSmemLimit) {
-        h->smem_axes = false;  // axes live in global memory (L1/L2-cached); tables can be generous
-        per_cell = 2.0;
-    } else {
-        h->smem_axes = true;
-        while (per_cell > 1.0 / 64 && total_bytes(per_cell) > kSmemPreferred) per_cell *= 0.5;
-        if (total_bytes(per_cell) > kSmemLimit) per_cell = 0.0;
+        lut_bytes += align_up((unsigned)(a.M * 8), 16);
     }
     std::vector<unsigned char> pack;
     for (int d = 0; d < n; ++d) {
         AxisMeta& a = h->ax[d];
-        const int L = (int)h->axis_len[d];
+        const int L = a.L;
         const void* nodes = h->axes_host[d].data();
-        a.L = L;
-        a.g0 = load_elem(h->dtype, nodes, 0);
-        a.gl = load_elem(h->dtype, nodes, L - 1);
-        int M = (int)std::min<double>(std::max(1.0, per_cell * (double)L), h->dtype == NINT_F64 ? 16777216.0 : 1048576.0);
-        double inv_w = 0.0;
-        const double span = a.gl - a.g0;
-        if (L >= 2 && M >= 2 && std::isfinite(span) && span > 0.0) {
-            inv_w = (double)M / span;
-            if (h->dtype == NINT_F32) inv_w = (double)(float)inv_w;  // the device multiplies by this in T
-            const double w = 1.0 / inv_w;
-            if (!std::isfinite(inv_w) || !(inv_w > 0.0) || !std::isfinite(w) || !(w > 0.0)) inv_w = 0.0;
-        }
-        if (inv_w == 0.0) M = 1;  // degenerate axis: one bucket, plain binary search over all nodes
-        a.M = M;
-        a.inv_w = inv_w;
-        std::vector<uint2> lut;
-        build_lut(h->dtype, nodes, L, M, a.g0, inv_w, lut);
-        // nodes, followed by two +inf pads (count_less may look one and two nodes past its upper bound)
+        // records {node, cell reciprocal}; two {+inf, 0} pads (the bracket may look one and two nodes past
+        // its upper bound).  Reciprocals only for cells whose width is comfortably normal (div_markstein).
         a.node_off = (unsigned)pack.size();
-        pack.resize(pack.size() + align_up((unsigned)((L + 2) * es), 16), 0);
-        std::memcpy(pack.data() + a.node_off, nodes, (size_t)L * es);
-        for (int k = 0; k < 2; ++k) {
+        pack.resize(pack.size() + align_up((unsigned)((L + 2) * 2 * es), 16), 0);
+        for (int l = 0; l < L + 2; ++l) {
+            unsigned char* rec = pack.data() + a.node_off + (size_t)l * 2 * es;
             if (h->dtype == NINT_F64) {
-                const double inf = std::numeric_limits<double>::infinity();
-                std::memcpy(pack.data() + a.node_off + (size_t)(L + k) * es, &inf, es);
+                const double* g = (const double*)nodes;
+                double node = l < L ? g[l] : std::numeric_limits<double>::infinity();
+                double r = 0.0;
+                if (l + 1 < L) {
+                    const double w = g[l + 1] - g[l];
+                    if (w >= 0x1p-500 && w < 0x1p500) r = 1.0 / w;
+                }
+                std::memcpy(rec, &node, es);
+                std::memcpy(rec + es, &r, es);
             } else {
-                const float inf = std::numeric_limits<float>::infinity();
-                std::memcpy(pack.data() + a.node_off + (size_t)(L + k) * es, &inf, es);
+                const float* g = (const float*)nodes;
+                float node = l < L ? g[l] : std::numeric_limits<float>::infinity();
+                float r = 0.0f;
+                if (l + 1 < L) {
+                    const float w = g[l + 1] - g[l];
+                    if (w >= 0x1p-60f && w < 0x1p60f) r = 1.0f / w;
+                }
+                std::memcpy(rec, &node, es);
+                std::memcpy(rec + es, &r, es);
             }
         }
         a.lut_off = (unsigned)pack.size();
-        pack.resize(pack.size() + align_up((unsigned)(M * 8), 16), 0);
-        std::memcpy(pack.data() + a.lut_off, lut.data(), (size_t)M * 8);
-        // per-cell reciprocals for div_cell(): only cells whose width is comfortably normal
-        a.rcp_off = (unsigned)pack.size();
-        pack.resize(pack.size() + align_up((unsigned)(L * es), 16), 0);
-        for (int l = 0; l + 1 < L; ++l) {
-            if (h->dtype == NINT_F64) {
-                const double w = ((const double*)nodes)[l + 1] - ((const double*)nodes)[l];
-                double r = 0.0;
-                if (w >= 0x1p-500 && w < 0x1p500) r = 1.0 / w;
-                std::memcpy(pack.data() + a.rcp_off + (size_t)l * es, &r, es);
-            } else {
-                const float w = ((const float*)nodes)[l + 1] - ((const float*)nodes)[l];
-                float r = 0.0f;
-                if (w >= 0x1p-60f && w < 0x1p60f) r = 1.0f / w;
-                std::memcpy(pack.data() + a.rcp_off + (size_t)l * es, &r, es);
-            }
-        }
+        pack.resize(pack.size() + align_up((unsigned)(a.M * 8), 16), 0);
+        std::memcpy(pack.data() + a.lut_off, luts[d].data(), (size_t)a.M * 8);
     }
     h->pack_bytes = (unsigned)pack.size();
     if (h->pack_bytes == 0) return NINT_OK;
@@ -328,9 +370,62 @@ int upload_values(nint_handle* h, const void* values_host, const ptrdiff_t* stri
 
 // ------------------------------------------------------------------------------- launching
 template <class T>
+void fill_params(const nint_handle* h, nint::Params<T>& P);
+
+// Cell-packed copy of the value table for Linear: cell (l_0..l_{N-1}) owns its 2^N corners as one
+// contiguous aligned block, so a point costs one 2^N*sizeof(T)-byte access instead of 2^(N-1) scattered
+// row segments.  It multiplies the table's footprint by about 2^N, so it is only built when that fits a
+// share of free device memory; NINT_PACK=0 disables it, NINT_PACK=1 forces it (memory permitting).
+int build_cells(nint_handle* h) {
+    if (h->d_cells || h->constant || h->strategy != NINT_LINEAR) return NINT_OK;
+    const char* env = std::getenv("NINT_PACK");
+    if (env && std::atoi(env) == 0) return NINT_OK;
+    const int n = h->ndim_eff;
+    const size_t es = elem_size(h->dtype);
+    unsigned long long cells = 1;
+    for (int d = 0; d < n; ++d) {
+        if (h->axis_len[d] < 2) return NINT_OK;
+        cells *= (unsigned long long)(h->axis_len[d] - 1);
+    }
+    const unsigned long long total = cells << n;
+    const unsigned long long bytes = total * es;
+    size_t free_b = 0, total_b = 0;
+    NINT_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (bytes > free_b / 4 || n > 6) return NINT_OK;
+    long long stride = 1;
+    for (int d = n - 1; d >= 0; --d) {
+        h->ax[d].cstride = stride;
+        stride *= (long long)(h->axis_len[d] - 1);
+    }
+    void* out = nullptr;
+    if (cudaMalloc(&out, (size_t)bytes + 64) != cudaSuccess) {
+        cudaGetLastError();
+        return NINT_OK;  // not enough memory: keep the plain layout
+    }
+    cudaError_t e;
+    if (h->dtype == NINT_F64) {
+        nint::Params<double> P;
+        fill_params<double>(h, P);
+        e = nint::launch_pack_cells<double>(P, n, (double*)out, total, h->sm_count, nullptr);
+    } else {
+        nint::Params<float> P;
+        fill_params<float>(h, P);
+        e = nint::launch_pack_cells<float>(P, n, (float*)out, total, h->sm_count, nullptr);
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(out);
+        return cuda_fail(e, "pack_cells");
+    }
+    h->d_cells = out;
+    return NINT_OK;
+}
+
+template <class T>
 void fill_params(const nint_handle* h, nint::Params<T>& P) {
     std::memset(&P, 0, sizeof P);
     P.values = (const T*)h->d_values;
+    P.cells = (h->strategy == NINT_LINEAR) ? (const T*)h->d_cells : nullptr;
     P.pack = h->d_pack;
     P.pack_bytes = h->pack_bytes;
     P.fill = (T)h->fill;
@@ -342,11 +437,13 @@ void fill_params(const nint_handle* h, nint::Params<T>& P) {
         P.M[d] = a.M;
         P.node_off[d] = a.node_off;
         P.lut_off[d] = a.lut_off;
-        P.rcp_off[d] = a.rcp_off;
         P.vstride[d] = a.vstride;
+        P.cstride[d] = a.cstride;
         P.g0[d] = (T)a.g0;
         P.gl[d] = (T)a.gl;
         P.inv_w[d] = (T)a.inv_w;
+        P.inv_h[d] = (T)a.inv_h;
+        P.flags[d] = a.flags;
     }
 }
 
@@ -371,7 +468,6 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     cfg.ndim = h->ndim_eff;
     cfg.is_nd = h->kind == NINT_KIND_ND;
     cfg.strategy = h->strategy;
-    cfg.extrap = h->extrap;
     cfg.smem_axes = h->smem_axes;
     cfg.smem_bytes = h->pack_bytes;
     cfg.sm_count = h->sm_count;
@@ -539,6 +635,7 @@ int nint_create(int device, int kind, int dtype, int ngrid, const size_t* axis_l
     }
     rc = upload_values(h, values_host, value_strides);
     if (rc == NINT_OK && !h->constant) rc = build_pack(h);
+    if (rc == NINT_OK) rc = build_cells(h);
     if (rc == NINT_OK) {
         cudaError_t e2 = cudaMalloc((void**)&h->d_info, sizeof(nint_batch_info));
         if (e2 == cudaSuccess) e2 = cudaMalloc(&h->d_pt, NINT_MAX_NDIM * sizeof(double));
@@ -559,6 +656,7 @@ void nint_destroy(nint_handle* h) {
         DeviceGuard guard(h->device);
         free_pipeline(h);
         if (h->d_values) cudaFree(h->d_values);
+        if (h->d_cells) cudaFree(h->d_cells);
         if (h->d_pack) cudaFree(h->d_pack);
         if (h->d_info) cudaFree(h->d_info);
         if (h->d_pt) cudaFree(h->d_pt);
@@ -599,7 +697,12 @@ int nint_set_strategy(nint_handle* h, int strategy) {
         return fail(NINT_E_UNSUPPORTED, -1, "LeftNearest/RightNearest exist for Interp1D only");
     // three/mod.rs:259-271: the strategy is replaced first, then checked (and stays replaced on error)
     h->strategy = strategy;
-    return check_extrapolate(h, h->extrap, h->extrap);
+    int rc = check_extrapolate(h, h->extrap, h->extrap);
+    if (rc == NINT_OK && strategy == NINT_LINEAR && !h->d_cells) {
+        DeviceGuard guard(h->device);
+        if (guard.ok) rc = build_cells(h);
+    }
+    return rc;
 }
 
 int nint_interpolate_batch(nint_handle* h, const void* const* coords, size_t n, void* out, uint8_t* status,

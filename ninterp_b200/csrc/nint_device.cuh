@@ -4,15 +4,23 @@
 //   front-end  interpolator/{one,two,three,n}/mod.rs  (bounds test + Extrapolate policy)
 //   bracket    strategy/traits.rs:10-33                (find_nearest_index)
 //   strategies interpolator/{one,two,three,n}/strategies.rs
-// Every arithmetic step is a single IEEE round-to-nearest operation in T: this translation unit
-// must be compiled with -fmad=false (Rust never contracts a*b+c) and without -use_fast_math.
+// Every arithmetic step of the reference is a single IEEE round-to-nearest operation in T: this
+// translation unit must be compiled with -fmad=false (Rust never contracts a*b+c) and without
+// -use_fast_math.  The only FMAs are explicit ones inside div_markstein(), which reproduce IEEE division.
+//
+// Structure of a point's evaluation
+//   fast path   guess the cell on every axis, VERIFY it against the node values (g[k] < p <= g[k+1]),
+//               gather the cell, blend.  A verified cell implies the point is in range and finite, so
+//               the fast path is the same for every Extrapolate policy.
+//   general     everything else (out of range, NaN/inf, exact node hits, degenerate axes, duplicate
+//               nodes, wide buckets): an out-of-line restatement of the reference's control flow.
 //
 // Data layout in HBM
 //   coords   struct of arrays (one column per axis) or array of [T;N] points (coord_stride)
-//   values   dense C-order table, last axis fastest: the 2^N corners of a cell are 2^(N-1)
-//            pairs of adjacent elements
-//   pack     per axis: the L nodes followed by an M-entry bucket table; staged once per CTA in
-//            shared memory so the bracket search never leaves the SM
+//   values   dense C-order table, last axis fastest
+//   cells    optional cell-packed copy for Linear: the 2^N corners of each cell contiguous and aligned
+//   pack     per axis: L nodes (+2 pads), an M-entry bucket table, L cell reciprocals; staged once per
+//            CTA in shared memory so the bracket search never leaves the SM
 #pragma once
 #include <cuda_runtime.h>
 
@@ -24,7 +32,10 @@ namespace nint {
 
 constexpr int kMaxDim = NINT_MAX_NDIM;
 constexpr int kBlock = 256;
-constexpr int kExtrapRuntime = -1;
+
+// per-axis flags (Params::flags)
+constexpr int kAxisUniform = 1;  // nodes are evenly spaced to within a small fraction of a cell
+constexpr int kAxisFast = 2;     // axis may use the fast path (>= 2 nodes, strictly increasing)
 
 template <class T>
 struct Params {
@@ -34,30 +45,48 @@ struct Params {
     uint8_t* status;
     nint_batch_info* info;
     const T* values;
-    const unsigned char* pack;  // axis pack in global memory (nodes + bucket tables)
-    unsigned pack_bytes;        // multiple of 16
+    const T* cells;              // cell-packed copy of the table (2^N corners per cell, contiguous) or NULL
+    const unsigned char* pack;   // axis pack in global memory
+    unsigned pack_bytes;         // multiple of 16
     unsigned long long n;
     unsigned long long index_base;  // batch index of point 0 (host pipeline chunks)
     T fill;
-    int extrap;  // policy when the kernel is instantiated with EXTRAP == kExtrapRuntime
+    int extrap;
     float l2_frac;  // fraction of the value table kept evict_last in L2 (0 = no hint)
     int L[kMaxDim];
     int M[kMaxDim];
-    unsigned node_off[kMaxDim];  // byte offsets into the pack
+    int flags[kMaxDim];
+    unsigned node_off[kMaxDim];  // byte offsets into the pack: {node, cell reciprocal} records
     unsigned lut_off[kMaxDim];
-    unsigned rcp_off[kMaxDim];   // per cell l: RN(1 / (g[l+1] - g[l])), or 0 when outside the safe window
     long long vstride[kMaxDim];  // element strides of `values`
-    T g0[kMaxDim], gl[kMaxDim], inv_w[kMaxDim];
+    long long cstride[kMaxDim];  // cell strides of `cells` (in cells)
+    T g0[kMaxDim], gl[kMaxDim];
+    T inv_w[kMaxDim];            // buckets per unit length (bucket table)
+    T inv_h[kMaxDim];            // cells per unit length (uniform axes)
 };
 
 template <class T>
 struct AxisRef {
-    const T* g;        // L nodes followed by two +inf pads
-    const uint2* lut;  // bucket b -> [lo, hi]: the node count below any point of the bucket
-    const T* rcp;      // rcp[l] = RN(1 / (g[l+1] - g[l])) for cells inside the safe exponent window, else 0
-    int L, M;
-    T g0, gl, inv_w;
+    const T* rec;      // L+2 records {node, rcp}: rec[2l] = g[l] (two +inf pads at the end),
+                       // rec[2l+1] = RN(1 / (g[l+1] - g[l])) for cells inside the safe exponent window, else 0
+    const uint2* lut;  // bucket b -> [lo, hi]: bounds on the node count below any point of the bucket
+    int L, M, flags;
+    T g0, gl, inv_w, inv_h;
+    __device__ __forceinline__ T g(int i) const { return rec[2 * i]; }
+    __device__ __forceinline__ T rcp(int i) const { return rec[2 * i + 1]; }
 };
+
+// {g[k], rcp[k]} with one 2-element shared/global load
+__device__ __forceinline__ void ld_rec(const double* p, double& g, double& r) {
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    g = v.x;
+    r = v.y;
+}
+__device__ __forceinline__ void ld_rec(const float* p, float& g, float& r) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    g = v.x;
+    r = v.y;
+}
 
 __device__ __forceinline__ int to_int_sat(float x) { return __float2int_rz(x); }    // NaN -> 0
 __device__ __forceinline__ int to_int_sat(double x) { return __double2int_rz(x); }  // saturating
@@ -76,9 +105,7 @@ __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
 template <class T>
 __device__ __forceinline__ void st_stream(T* p, T v) { __stcs(p, v); }
 
-// Value-table loads carry an L2 cache policy: a fraction of the table's lines is held evict_last,
-// the rest evict_first, so that a table larger than L2 keeps a stable resident subset instead of
-// thrashing one 32-byte sector per 128-byte line ("L2 residency").
+// Value-table loads carry an L2 cache policy (a fraction of the lines evict_last, the rest evict_first).
 __device__ __forceinline__ unsigned long long make_table_policy(float frac) {
     unsigned long long pol;
     if (frac > 0.0f) {
@@ -103,6 +130,62 @@ __device__ __forceinline__ void ld_table2(const double* p, unsigned long long po
 }
 __device__ __forceinline__ void ld_table2(const float* p, unsigned long long pol, float& a, float& b) {
     asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(a), "=f"(b) : "l"(p), "l"(pol));
+}
+
+// One cell of the cell-packed table: COUNT = 2^N contiguous elements, loaded 32 bytes at a time
+// (LDG.256 on sm_100) or with the widest load the block size allows.
+template <int COUNT>
+__device__ __forceinline__ void ld_block(const double* p, unsigned long long pol, double (&v)[COUNT]) {
+    if constexpr (COUNT >= 4) {
+#pragma unroll
+        for (int k = 0; k < COUNT; k += 4)
+            asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                         : "=d"(v[k]), "=d"(v[k + 1]), "=d"(v[k + 2]), "=d"(v[k + 3]) : "l"(p + k), "l"(pol));
+    } else {
+        ld_table2(p, pol, v[0], v[1]);
+    }
+}
+template <int COUNT>
+__device__ __forceinline__ void ld_block(const float* p, unsigned long long pol, float (&v)[COUNT]) {
+    if constexpr (COUNT >= 8) {
+#pragma unroll
+        for (int k = 0; k < COUNT; k += 8)
+            asm volatile("ld.global.nc.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                         : "=f"(v[k]), "=f"(v[k + 1]), "=f"(v[k + 2]), "=f"(v[k + 3]), "=f"(v[k + 4]), "=f"(v[k + 5]),
+                           "=f"(v[k + 6]), "=f"(v[k + 7]) : "l"(p + k), "l"(pol));
+    } else if constexpr (COUNT == 4) {
+        asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p), "l"(pol));
+    } else {
+        ld_table2(p, pol, v[0], v[1]);
+    }
+}
+
+// Same, without a cache policy operand (plain LRU): used for the cell-packed table.
+template <int COUNT>
+__device__ __forceinline__ void ld_cells(const double* p, double (&v)[COUNT]) {
+    if constexpr (COUNT >= 4) {
+#pragma unroll
+        for (int k = 0; k < COUNT; k += 4)
+            asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                         : "=d"(v[k]), "=d"(v[k + 1]), "=d"(v[k + 2]), "=d"(v[k + 3]) : "l"(p + k));
+    } else {
+        asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+    }
+}
+template <int COUNT>
+__device__ __forceinline__ void ld_cells(const float* p, float (&v)[COUNT]) {
+    if constexpr (COUNT >= 8) {
+#pragma unroll
+        for (int k = 0; k < COUNT; k += 8)
+            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(v[k]), "=f"(v[k + 1]), "=f"(v[k + 2]), "=f"(v[k + 3]), "=f"(v[k + 4]), "=f"(v[k + 5]),
+                           "=f"(v[k + 6]), "=f"(v[k + 7]) : "l"(p + k));
+    } else if constexpr (COUNT == 4) {
+        asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+    } else {
+        asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "l"(p));
+    }
 }
 
 // Two adjacent table elements row[0], row[1] with one aligned vector load; when `row` sits in the upper
@@ -131,15 +214,9 @@ __device__ __forceinline__ int count_less(const AxisRef<T>& a, T p) {
     const uint2 e = a.lut[b];
     int lo = (int)e.x;
     int n = (int)e.y - (int)e.x;
-    if (n <= 2) {
-        // nodes at or beyond the upper bound are >= p and the two pads are +inf: count two unconditionally
-        const T n0 = a.g[lo];
-        const T n1 = a.g[lo + 1];
-        return lo + (n0 < p ? 1 : 0) + (n1 < p ? 1 : 0);
-    }
     while (n > 0) {
         const int half = n >> 1;
-        const bool lt = a.g[lo + half] < p;
+        const bool lt = a.g(lo + half) < p;
         lo = lt ? lo + half + 1 : lo;
         n = lt ? n - half - 1 : half;
     }
@@ -149,29 +226,39 @@ __device__ __forceinline__ int count_less(const AxisRef<T>& a, T p) {
 // a / w, correctly rounded, for a cell whose reciprocal r = RN(1/w) was prepared on the host.
 // q0 = RN(a*r) is within 2 ulp of a/w; one FMA residual step makes it faithful and a second one
 // (Markstein's theorem, r being the correctly rounded reciprocal) makes it the correctly rounded
-// quotient, i.e. bit-identical to the IEEE division the reference performs.  The exponent window
-// (|a|, w in [2^-500, 2^500) for f64, [2^-60, 2^60) for f32) keeps every intermediate normal; anything
-// else (zero, subnormal, huge, inf, NaN, or r == 0 from the host) takes the hardware division.
-__device__ __forceinline__ double div_cell(double a, double w, double r) {
-    const unsigned hi = (unsigned)__double2hiint(a) & 0x7fffffffu;
-    if ((hi - 0x20b00000u) < 0x3e800000u && r != 0.0) {
-        double q = a * r;
-        double e = __fma_rn(-q, w, a);
-        q = __fma_rn(e, r, q);
-        e = __fma_rn(-q, w, a);
-        return __fma_rn(e, r, q);
-    }
-    return a / w;
+// quotient, i.e. bit-identical to the IEEE division the reference performs.  Only valid inside the
+// exponent window checked by in_div_window(); nint_selftest_divide() compares it with `a / w`.
+template <class T>
+__device__ __forceinline__ T div_markstein(T a, T w, T r);
+template <>
+__device__ __forceinline__ double div_markstein<double>(double a, double w, double r) {
+    double q = a * r;
+    double e = __fma_rn(-q, w, a);
+    q = __fma_rn(e, r, q);
+    e = __fma_rn(-q, w, a);
+    return __fma_rn(e, r, q);
 }
-__device__ __forceinline__ float div_cell(float a, float w, float r) {
+template <>
+__device__ __forceinline__ float div_markstein<float>(float a, float w, float r) {
+    float q = a * r;
+    float e = __fmaf_rn(-q, w, a);
+    q = __fmaf_rn(e, r, q);
+    e = __fmaf_rn(-q, w, a);
+    return __fmaf_rn(e, r, q);
+}
+// |a| in [2^-500, 2^500) for f64, [2^-60, 2^60) for f32: with w in the same window (host side, r != 0)
+// every intermediate of div_markstein() stays normal.
+__device__ __forceinline__ bool in_div_window(double a) {
+    const unsigned hi = (unsigned)__double2hiint(a) & 0x7fffffffu;
+    return (hi - 0x20b00000u) < 0x3e800000u;
+}
+__device__ __forceinline__ bool in_div_window(float a) {
     const unsigned bits = (unsigned)__float_as_int(a) & 0x7fffffffu;
-    if ((bits - 0x21800000u) < 0x3c000000u && r != 0.0f) {
-        float q = a * r;
-        float e = __fmaf_rn(-q, w, a);
-        q = __fmaf_rn(e, r, q);
-        e = __fmaf_rn(-q, w, a);
-        return __fmaf_rn(e, r, q);
-    }
+    return (bits - 0x21800000u) < 0x3c000000u;
+}
+template <class T>
+__device__ __forceinline__ T div_cell(T a, T w, T r) {
+    if (in_div_window(a) && r != T(0)) return div_markstein<T>(a, w, r);
     return a / w;
 }
 
@@ -191,8 +278,66 @@ __device__ __forceinline__ T clamp_coord(T x, T lo, T hi) {
     return (x < lo) ? lo : ((x > hi) ? hi : x);
 }
 
+// Axis d as seen by the kernel.  Built at the point of use from the kernel parameters (constant bank),
+// so that nothing about the axes has to stay in registers across the point loop.
+template <class T>
+__device__ __forceinline__ AxisRef<T> load_axis(const Params<T>& P, const unsigned char* pack, int d) {
+    AxisRef<T> a;
+    a.rec = reinterpret_cast<const T*>(pack + P.node_off[d]);
+    a.lut = reinterpret_cast<const uint2*>(pack + P.lut_off[d]);
+    a.L = P.L[d];
+    a.M = P.M[d];
+    a.flags = P.flags[d];
+    a.g0 = P.g0[d];
+    a.gl = P.gl[d];
+    a.inv_w = P.inv_w[d];
+    a.inv_h = P.inv_h[d];
+    return a;
+}
+template <class T, int N>
+__device__ __forceinline__ void load_axes(const Params<T>& P, const unsigned char* pack, AxisRef<T> (&ax)[N]) {
+#pragma unroll
+    for (int d = 0; d < N; ++d) ax[d] = load_axis<T>(P, pack, d);
+}
+
+template <class T, int N>
+struct Point {
+    T v[N];
+};
+template <class T>
+struct Outcome {
+    T value;
+    unsigned status;
+};
+
+// The 2^(N-1) rows of a cell in the plain table (rows run along the last axis, stride 1).
+// Row r: bit (N-2-d) of r selects the upper node of axis d, so axis 0 is the most significant bit.
+template <class T, int N>
+__device__ __forceinline__ void gather_rows(const T* base, const long long (&step)[N], unsigned long long pol,
+                                            bool last_fixed, T (&cube)[1 << N]) {
+    constexpr int kRows = 1 << (N - 1);
+    const T* rowp[kRows];
+    rowp[0] = base;
+#pragma unroll
+    for (int r = 1; r < kRows; ++r) {
+        const int low = r & (-r);
+        int d = 0;
+#pragma unroll
+        for (int k = 0; k < N - 1; ++k)
+            if ((low >> (N - 2 - k)) & 1) d = k;
+        rowp[r] = rowp[r & (r - 1)] + step[d];
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        T lo, hi;
+        ld_pair(rowp[r], pol, lo, hi);
+        cube[2 * r] = lo;
+        cube[2 * r + 1] = last_fixed ? lo : hi;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
-// Strategies.  `status` is set to NINT_STATUS_PANIC where the reference would index out of
+// General path.  `status` is set to NINT_STATUS_PANIC where the reference would index out of
 // bounds; the returned value is then unspecified (the caller writes a quiet NaN).
 //
 // COLLAPSE  an axis whose coordinate equals a node is *selected*, not blended
@@ -200,10 +345,9 @@ __device__ __forceinline__ T clamp_coord(T x, T lo, T hi) {
 // LEN1      InterpND returns early when a single element is left after collapsing
 //           (n/strategies.rs:47-50), which also covers un-collapsed axes of length 1.
 // ---------------------------------------------------------------------------------------------
-template <class T, int N, bool COLLAPSE, bool LEN1, bool INRANGE>
-__device__ __forceinline__ T eval_linear(const AxisRef<T> (&ax)[N], const long long (&vs)[N],
-                                         const T* __restrict__ values, unsigned long long pol, const T (&q)[N],
-                                         unsigned& status) {
+template <class T, int N, bool COLLAPSE, bool LEN1>
+__device__ __forceinline__ T eval_linear(const AxisRef<T> (&ax)[N], const Params<T>& P, unsigned long long pol,
+                                         const T (&q)[N], unsigned& status) {
     int idx[N];
     T t[N];
     bool fixed[N];
@@ -212,12 +356,11 @@ __device__ __forceinline__ T eval_linear(const AxisRef<T> (&ax)[N], const long l
 #pragma unroll
     for (int d = 0; d < N; ++d) {
         const T p = q[d];
-        // INRANGE: the front-end already established g0 <= p <= gl, so p is not NaN
-        const bool isnan = INRANGE ? false : (p != p);
+        const bool isnan = (p != p);
         const int L = ax[d].L;
         const int c = isnan ? 0 : count_less(ax[d], p);
         bool hit = false;
-        if (COLLAPSE) hit = !isnan && c < L && ax[d].g[c] == p;
+        if (COLLAPSE) hit = !isnan && c < L && ax[d].g(c) == p;
         fixed[d] = hit;
         idx[d] = hit ? c : 0;
         t[d] = T(0);
@@ -229,42 +372,27 @@ __device__ __forceinline__ T eval_linear(const AxisRef<T> (&ax)[N], const long l
                 panic = true;
             } else {
                 const int l = (p >= ax[d].gl) ? L - 2 : max(c, 1) - 1;
-                const T gl_ = ax[d].g[l];
-                const T gu_ = ax[d].g[l + 1];
+                const T gl_ = ax[d].g(l);
+                const T gu_ = ax[d].g(l + 1);
                 idx[d] = l;
-                t[d] = div_cell(p - gl_, gu_ - gl_, ax[d].rcp[l]);
+                t[d] = div_cell(p - gl_, gu_ - gl_, ax[d].rcp(l));
             }
         }
     }
     long long base = 0;
+    long long step[N];
 #pragma unroll
-    for (int d = 0; d < N; ++d) base += (long long)idx[d] * vs[d];
-    if (LEN1 && single) return ld_table(values + base, pol);
+    for (int d = 0; d < N; ++d) {
+        base += (long long)idx[d] * P.vstride[d];
+        step[d] = fixed[d] ? 0 : P.vstride[d];
+    }
+    if (LEN1 && single) return ld_table(P.values + base, pol);
     if (panic) {
         status = NINT_STATUS_PANIC;
         return T(0);
     }
-    // Gather the cell as 2^(N-1) rows of two elements adjacent along the last axis (stride 1).
-    // Row r: bit (N-2-d) of r selects the upper node of axis d, so axis 0 is the most significant bit.
-    constexpr int kRows = 1 << (N - 1);
-    const T* rowp[kRows];
-    rowp[0] = values + base;
-#pragma unroll
-    for (int r = 1; r < kRows; ++r) {
-        const int low = r & (-r);          // lowest set bit
-        int d = 0;
-#pragma unroll
-        for (int k = 0; k < N - 1; ++k) if ((low >> (N - 2 - k)) & 1) d = k;
-        rowp[r] = rowp[r & (r - 1)] + (fixed[d] ? 0 : vs[d]);
-    }
     T cube[1 << N];
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-        T lo, hi;
-        ld_pair(rowp[r], pol, lo, hi);
-        cube[2 * r] = lo;
-        cube[2 * r + 1] = fixed[N - 1] ? lo : hi;
-    }
+    gather_rows<T, N>(P.values + base, step, pol, fixed[N - 1], cube);
     // reduce axis 0 first, then 1, ...: v_l * (1 - t) + v_u * t, each op rounded separately
 #pragma unroll
     for (int d = 0; d < N; ++d) {
@@ -282,9 +410,8 @@ __device__ __forceinline__ T eval_linear(const AxisRef<T> (&ax)[N], const long l
 
 // NEAREST (N-D and hard-coded) and, for N == 1, LEFT_NEAREST / RIGHT_NEAREST
 template <class T, int N, bool COLLAPSE, bool LEN1, int STRAT>
-__device__ __forceinline__ T eval_index(const AxisRef<T> (&ax)[N], const long long (&vs)[N],
-                                        const T* __restrict__ values, unsigned long long pol, const T (&q)[N],
-                                        unsigned& status) {
+__device__ __forceinline__ T eval_index(const AxisRef<T> (&ax)[N], const Params<T>& P, unsigned long long pol,
+                                        const T (&q)[N], unsigned& status) {
     int idx[N];
     bool panic = false;
     bool single = true;
@@ -295,7 +422,7 @@ __device__ __forceinline__ T eval_index(const AxisRef<T> (&ax)[N], const long lo
         const int L = ax[d].L;
         const int c = isnan ? 0 : count_less(ax[d], p);
         bool hit = false;
-        if (COLLAPSE) hit = !isnan && c < L && ax[d].g[c] == p;
+        if (COLLAPSE) hit = !isnan && c < L && ax[d].g(c) == p;
         idx[d] = hit ? c : 0;
         if (!hit) {
             single = single && (L == 1);
@@ -305,8 +432,8 @@ __device__ __forceinline__ T eval_index(const AxisRef<T> (&ax)[N], const long lo
                     panic = true;
                 } else {
                     const int l = (p == ax[d].gl) ? L - 2 : max(c, 1) - 1;
-                    const T gl_ = ax[d].g[l];
-                    const T gu_ = ax[d].g[l + 1];
+                    const T gl_ = ax[d].g(l);
+                    const T gu_ = ax[d].g(l + 1);
                     idx[d] = ((p - gl_) < (gu_ - p)) ? l : l + 1;
                 }
             } else {
@@ -323,24 +450,117 @@ __device__ __forceinline__ T eval_index(const AxisRef<T> (&ax)[N], const long lo
     }
     long long off = 0;
 #pragma unroll
-    for (int d = 0; d < N; ++d) off += (long long)idx[d] * vs[d];
-    if (LEN1 && single) return ld_table(values + off, pol);  // un-collapsed length-1 axes sit at index 0
+    for (int d = 0; d < N; ++d) off += (long long)idx[d] * P.vstride[d];
+    if (LEN1 && single) return ld_table(P.values + off, pol);  // un-collapsed length-1 axes sit at index 0
     if (panic) {
         status = NINT_STATUS_PANIC;
         return T(0);
     }
-    return ld_table(values + off, pol);
+    return ld_table(P.values + off, pol);
 }
 
-__device__ __forceinline__ unsigned long long shfl_down_u64(unsigned long long v, int delta) {
-    return __shfl_down_sync(0xffffffffu, v, delta);
+// Front-end + strategy for one point, exactly as the reference orders them.  Out of line on purpose:
+// it keeps the register allocation of the fast path small.
+template <class T, int N, bool IS_ND, int STRAT>
+__device__ __noinline__ Outcome<T> general_point(const Params<T>& P, const unsigned char* pack, Point<T, N> qin) {
+    AxisRef<T> ax[N];
+    load_axes<T, N>(P, pack, ax);
+    const unsigned long long pol = make_table_policy(P.l2_frac);
+    constexpr bool kCollapse = IS_ND || (N == 1);
+    constexpr bool kLen1 = IS_ND;
+    T q[N];
+    bool oob = false;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        q[d] = qin.v[d];
+        // !(first..=last).contains(p): NaN is out of bounds (three/mod.rs:198-201)
+        oob = oob || !(ax[d].g0 <= q[d] && q[d] <= ax[d].gl);
+    }
+    unsigned status = NINT_STATUS_OK;
+    T result = T(0);
+    bool done = false;
+    if (oob) {
+        const int extrap = P.extrap;
+        if (extrap == NINT_EXTRAPOLATE_FILL) {  // three/mod.rs:204
+            result = P.fill;
+            done = true;
+        } else if (extrap == NINT_EXTRAPOLATE_ERROR) {  // :225-236
+            status = NINT_STATUS_EXTRAPOLATE_ERROR;
+            done = true;
+        } else if (extrap == NINT_EXTRAPOLATE_CLAMP) {  // :205-214, every axis
+#pragma unroll
+            for (int d = 0; d < N; ++d) q[d] = clamp_coord(q[d], ax[d].g0, ax[d].gl);
+        } else if (extrap == NINT_EXTRAPOLATE_WRAP) {  // :215-224, every axis
+#pragma unroll
+            for (int d = 0; d < N; ++d) q[d] = wrap_coord(q[d], ax[d].g0, ax[d].gl);
+        }
+        // Enable: evaluate as is (:203)
+    }
+    if (!done) {
+        if (STRAT == NINT_LINEAR) result = eval_linear<T, N, kCollapse, kLen1>(ax, P, pol, q, status);
+        else result = eval_index<T, N, kCollapse, kLen1, STRAT>(ax, P, pol, q, status);
+    }
+    Outcome<T> o;
+    o.value = result;
+    o.status = status;
+    return o;
+}
+
+// Extrapolate::Wrap applied to every axis (three/mod.rs:215-224); out of line because of fmod.
+// Sets *oob when at least one coordinate is outside its axis (the condition for wrapping at all).
+template <class T, int N>
+__device__ __noinline__ Point<T, N> wrap_point(const Params<T>& P, Point<T, N> q, bool* oob) {
+    bool any = false;
+    Point<T, N> w;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        any = any || !(P.g0[d] <= q.v[d] && q.v[d] <= P.gl[d]);
+        w.v[d] = wrap_coord(q.v[d], P.g0[d], P.gl[d]);
+    }
+    *oob = any;
+    return w;
+}
+
+// Fast bracket of one axis: guess the cell, load its two nodes, and verify g[k] < p <= g[k+1]
+// (strictly below g[k+1] where an exact node hit must collapse the axis).  A verified cell is the cell
+// the reference picks: find_nearest_index returns the cell to the left of an exact hit, and `== last`
+// maps to L-2, both of which satisfy the same inequality when nodes are strictly increasing.
+template <class T, bool STRICT>
+__device__ __forceinline__ bool locate_fast(const AxisRef<T>& a, T p, int& k, T& G0, T& G1, T& R) {
+    bool ok = (a.flags & kAxisFast) != 0;
+    if (a.flags & kAxisUniform) {
+        k = to_int_sat((p - a.g0) * a.inv_h);
+    } else {
+        int b = to_int_sat((p - a.g0) * a.inv_w);
+        b = max(0, min(b, a.M - 1));
+        const uint2 e = a.lut[b];
+        const int lo = (int)e.x;
+        ok = ok && ((int)e.y - lo <= 2);
+        // nodes at or beyond the upper bound are >= p and the two pads are +inf: count two unconditionally
+        const T n0 = a.g(lo);
+        const T n1 = a.g(lo + 1);
+        k = lo + (n0 < p ? 1 : 0) + (n1 < p ? 1 : 0) - 1;
+    }
+    k = max(0, min(k, a.L - 2));
+    ld_rec(a.rec + 2 * k, G0, R);
+    G1 = a.g(k + 1);
+    return ok && (G0 < p) && (STRICT ? (p < G1) : (p <= G1));
 }
 
 // ---------------------------------------------------------------------------------------------
 // The kernel: persistent CTAs, grid-stride over the batch, one point per thread per trip.
 // ---------------------------------------------------------------------------------------------
-template <class T, int N, bool IS_ND, int STRAT, int EXTRAP, bool SMEM>
-__global__ void __launch_bounds__(kBlock) interp_kernel(const __grid_constant__ Params<T> P) {
+// Resident CTAs per SM the register allocator must leave room for: the fast path of the low-dimensional
+// kernels fits 64 registers (4 CTAs of 256 threads); the out-of-line general path may spill instead.
+#ifndef NINT_MIN_CTAS
+#define NINT_MIN_CTAS 4
+#endif
+constexpr int min_ctas(int n, int elem_bytes) {
+    return (n <= 3) ? NINT_MIN_CTAS : ((n == 4 || (n == 5 && elem_bytes == 4)) ? 2 : 1);
+}
+
+template <class T, int N, bool IS_ND, int STRAT, bool SMEM, bool CLAMP>
+__global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_kernel(const __grid_constant__ Params<T> P) {
     extern __shared__ __align__(16) unsigned char smem_pack[];
     const unsigned char* pack;
     if (SMEM) {
@@ -353,93 +573,118 @@ __global__ void __launch_bounds__(kBlock) interp_kernel(const __grid_constant__ 
         pack = P.pack;
     }
 
-    AxisRef<T> ax[N];
-    long long vs[N];
-#pragma unroll
-    for (int d = 0; d < N; ++d) {
-        ax[d].g = reinterpret_cast<const T*>(pack + P.node_off[d]);
-        ax[d].lut = reinterpret_cast<const uint2*>(pack + P.lut_off[d]);
-        ax[d].rcp = reinterpret_cast<const T*>(pack + P.rcp_off[d]);
-        ax[d].L = P.L[d];
-        ax[d].M = P.M[d];
-        ax[d].g0 = P.g0[d];
-        ax[d].gl = P.gl[d];
-        ax[d].inv_w = P.inv_w[d];
-        vs[d] = P.vstride[d];
-    }
-    const int extrap = (EXTRAP == kExtrapRuntime) ? P.extrap : EXTRAP;
     constexpr bool kCollapse = IS_ND || (N == 1);
-    constexpr bool kLen1 = IS_ND;
-    // under Error and Fill only in-range (hence non-NaN) points reach the strategy
-    constexpr bool kInRange = (EXTRAP == NINT_EXTRAPOLATE_ERROR) || (EXTRAP == NINT_EXTRAPOLATE_FILL);
     const unsigned long long pol = make_table_policy(P.l2_frac);
 
-    unsigned long long n_err = 0, n_panic = 0;
-    unsigned long long first_err = ~0ull, first_panic = ~0ull;
+    // per-CTA failure counters live in shared memory (failures are the rare case; no registers held)
+    __shared__ unsigned long long s_info[4];  // n_error, n_panic, first_error, first_panic
+    if (threadIdx.x < 4) s_info[threadIdx.x] = (threadIdx.x < 2) ? 0ull : ~0ull;
+    __syncthreads();
 
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-        T q[N];
-        bool oob = false;
+        Point<T, N> q;
 #pragma unroll
-        for (int d = 0; d < N; ++d) {
-            q[d] = ld_stream(P.coords[d] + i * P.coord_stride);
-            // !(first..=last).contains(p): NaN is out of bounds (three/mod.rs:198-201)
-            oob = oob || !(ax[d].g0 <= q[d] && q[d] <= ax[d].gl);
-        }
+        for (int d = 0; d < N; ++d) q.v[d] = ld_stream(P.coords[d] + i * P.coord_stride);
+
+        // ---- fast path: bracket every axis, verified against the nodes.  Under Extrapolate::Wrap a point
+        // that fails is wrapped (if it is out of range) and gets one more attempt before the general path.
         unsigned status = NINT_STATUS_OK;
         T result;
-        bool done = false;
-        if (oob) {
-            if (extrap == NINT_EXTRAPOLATE_FILL) {  // three/mod.rs:204
-                result = P.fill;
-                done = true;
-            } else if (extrap == NINT_EXTRAPOLATE_ERROR) {  // :225-236
-                status = NINT_STATUS_EXTRAPOLATE_ERROR;
-                done = true;
-            } else if (extrap == NINT_EXTRAPOLATE_CLAMP) {  // :205-214, every axis
+        Point<T, N> pt = q;
+        bool retried = false;
+        for (;;) {
+            int k[N];
+            T t[N];
+            bool ok = true;
 #pragma unroll
-                for (int d = 0; d < N; ++d) q[d] = clamp_coord(q[d], ax[d].g0, ax[d].gl);
-            } else if (extrap == NINT_EXTRAPOLATE_WRAP) {  // :215-224, every axis
+            for (int d = 0; d < N; ++d) {
+                const AxisRef<T> ax = load_axis<T>(P, pack, d);
+                // Clamp touches every axis as soon as one is out of range and leaves in-range coordinates
+                // alone, so clamping up front is the same map (three/mod.rs:205-214)
+                const T p = CLAMP ? clamp_coord(pt.v[d], ax.g0, ax.gl) : pt.v[d];
+                T G0, G1, r;
+                ok = locate_fast<T, kCollapse>(ax, p, k[d], G0, G1, r) && ok;
+                t[d] = T(0);
+                if (STRAT == NINT_LINEAR) {
+                    const T a = p - G0;
+                    ok = ok && in_div_window(a) && (r != T(0));
+                    t[d] = div_markstein<T>(a, G1 - G0, r);
+                } else if (STRAT == NINT_NEAREST) {
+                    k[d] += ((p - G0) < (G1 - p)) ? 0 : 1;  // tie -> upper (three/strategies.rs:70-74)
+                } else if (STRAT == NINT_RIGHT_NEAREST) {
+                    k[d] += 1;
+                }
+            }
+            if (ok) {
+                if (STRAT == NINT_LINEAR) {
+                    T cube[1 << N];
+                    if (P.cells != nullptr) {
+                        long long cell = 0;
 #pragma unroll
-                for (int d = 0; d < N; ++d) q[d] = wrap_coord(q[d], ax[d].g0, ax[d].gl);
+                        for (int d = 0; d < N; ++d) cell += (long long)k[d] * P.cstride[d];
+                        ld_cells<(1 << N)>(P.cells + cell * (1 << N), cube);
+                    } else {
+                        long long base = 0;
+                        long long step[N];
+#pragma unroll
+                        for (int d = 0; d < N; ++d) {
+                            base += (long long)k[d] * P.vstride[d];
+                            step[d] = P.vstride[d];
+                        }
+                        gather_rows<T, N>(P.values + base, step, pol, false, cube);
+                    }
+#pragma unroll
+                    for (int d = 0; d < N; ++d) {
+                        const int half = 1 << (N - 1 - d);
+                        const T td = t[d];
+                        const T sd = T(1) - td;
+#pragma unroll
+                        for (int j = 0; j < half; ++j) cube[j] = cube[j] * sd + cube[half + j] * td;
+                    }
+                    result = cube[0];
+                } else {
+                    long long off = 0;
+#pragma unroll
+                    for (int d = 0; d < N; ++d) off += (long long)k[d] * P.vstride[d];
+                    result = ld_table(P.values + off, pol);
+                }
+                break;
             }
-            // Enable: evaluate as is (:203)
-        }
-        if (!done) {
-            if (STRAT == NINT_LINEAR) result = eval_linear<T, N, kCollapse, kLen1, kInRange>(ax, vs, P.values, pol, q, status);
-            else result = eval_index<T, N, kCollapse, kLen1, STRAT>(ax, vs, P.values, pol, q, status);
-        }
-        if (status != NINT_STATUS_OK) {
-            result = quiet_nan<T>();
-            if (status == NINT_STATUS_PANIC) {
-                ++n_panic;
-                first_panic = min(first_panic, i + P.index_base);
-            } else {
-                ++n_err;
-                first_err = min(first_err, i + P.index_base);
+            if (!retried && P.extrap == NINT_EXTRAPOLATE_WRAP) {
+                retried = true;
+                bool oob;
+                const Point<T, N> w = wrap_point<T, N>(P, q, &oob);
+                if (oob) {
+                    pt = w;
+                    continue;
+                }
             }
+            const Outcome<T> o = general_point<T, N, IS_ND, STRAT>(P, pack, q);
+            result = o.value;
+            status = o.status;
+            if (status != NINT_STATUS_OK) {
+                result = quiet_nan<T>();
+                const int slot = (status == NINT_STATUS_PANIC) ? 1 : 0;
+                atomicAdd(&s_info[slot], 1ull);
+                atomicMin(&s_info[2 + slot], i + P.index_base);
+            }
+            break;
         }
         st_stream(P.out + i, result);
         if (P.status) P.status[i] = (uint8_t)status;
     }
 
     if (P.info) {
-#pragma unroll
-        for (int delta = 16; delta > 0; delta >>= 1) {
-            n_err += shfl_down_u64(n_err, delta);
-            n_panic += shfl_down_u64(n_panic, delta);
-            first_err = min(first_err, shfl_down_u64(first_err, delta));
-            first_panic = min(first_panic, shfl_down_u64(first_panic, delta));
-        }
-        if ((threadIdx.x & 31) == 0) {
-            if (n_err) {
-                atomicAdd((unsigned long long*)&P.info->n_error, n_err);
-                atomicMin((unsigned long long*)&P.info->first_error, first_err);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (s_info[0]) {
+                atomicAdd((unsigned long long*)&P.info->n_error, s_info[0]);
+                atomicMin((unsigned long long*)&P.info->first_error, s_info[2]);
             }
-            if (n_panic) {
-                atomicAdd((unsigned long long*)&P.info->n_panic, n_panic);
-                atomicMin((unsigned long long*)&P.info->first_panic, first_panic);
+            if (s_info[1]) {
+                atomicAdd((unsigned long long*)&P.info->n_panic, s_info[1]);
+                atomicMin((unsigned long long*)&P.info->first_panic, s_info[3]);
             }
         }
     }
@@ -457,13 +702,32 @@ __global__ void __launch_bounds__(kBlock) constant_kernel(const T* __restrict__ 
     }
 }
 
+// Builds the cell-packed copy: out[cell * 2^N + corner] = values[(l + corner bits) . vstride].
+template <class T>
+__global__ void __launch_bounds__(kBlock) pack_cells_kernel(const T* __restrict__ values, T* __restrict__ out, int ndim,
+                                                            Params<T> P, unsigned long long total) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const int corners = 1 << ndim;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int corner = (int)(e & (unsigned long long)(corners - 1));
+        unsigned long long cell = e >> ndim;
+        long long src = 0;
+        for (int d = ndim - 1; d >= 0; --d) {
+            const unsigned long long nc = (unsigned long long)(P.L[d] - 1);
+            const unsigned long long l = cell % nc;
+            cell /= nc;
+            src += (long long)(l + ((corner >> (ndim - 1 - d)) & 1)) * P.vstride[d];
+        }
+        out[e] = values[src];
+    }
+}
+
 // Launch interface implemented by the per-(T, family) translation units.
 struct LaunchCfg {
     int ndim;
     int is_nd;
     int strategy;
-    int extrap;
-    int smem_axes;     // stage the axis pack in shared memory
+    int smem_axes;  // stage the axis pack in shared memory
     unsigned smem_bytes;
     int sm_count;
     void* stream;
@@ -473,6 +737,8 @@ template <class T>
 cudaError_t launch_fixed(const Params<T>& P, const LaunchCfg& cfg);
 template <class T>
 cudaError_t launch_nd(const Params<T>& P, const LaunchCfg& cfg);
+template <class T>
+cudaError_t launch_pack_cells(const Params<T>& P, int ndim, T* out, unsigned long long total, int sm_count, void* stream);
 template <class T>
 cudaError_t launch_constant(const T* values, T* out, uint8_t* status, unsigned long long n, int sm_count,
                             void* stream);

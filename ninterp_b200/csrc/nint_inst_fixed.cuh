@@ -1,7 +1,6 @@
 // nint_inst_fixed.cuh — instantiates the Interp1D/2D/3D kernels for NINT_T (included by
-// nint_fixed_f32.cu / nint_fixed_f64.cu).  The Extrapolate policy is a template argument on the
-// shared-memory path so that e.g. the Error kernel carries no fmod code; the global-memory
-// fallback (axes too large for shared memory) takes it at run time.
+// nint_fixed_f32.cu / nint_fixed_f64.cu): one kernel per (dimension, strategy, axes in shared or
+// global memory).  The Extrapolate policy only matters on the out-of-line general path.
 #include "nint_launch.cuh"
 
 namespace nint {
@@ -9,25 +8,15 @@ namespace nint {
 namespace {
 
 template <class T, int N, int STRAT>
-cudaError_t dispatch_extrap(const Params<T>& P, const LaunchCfg& cfg) {
-    if (!cfg.smem_axes) return launch_one<T, N, false, STRAT, kExtrapRuntime, false>(P, cfg);
-    switch (cfg.extrap) {
-    case NINT_EXTRAPOLATE_ENABLE:
-        if (STRAT == NINT_LINEAR) return launch_one<T, N, false, NINT_LINEAR, NINT_EXTRAPOLATE_ENABLE, true>(P, cfg);
-        return cudaErrorInvalidValue;  // rejected at construction (interpolator/mod.rs:88)
-    case NINT_EXTRAPOLATE_FILL: return launch_one<T, N, false, STRAT, NINT_EXTRAPOLATE_FILL, true>(P, cfg);
-    case NINT_EXTRAPOLATE_CLAMP: return launch_one<T, N, false, STRAT, NINT_EXTRAPOLATE_CLAMP, true>(P, cfg);
-    case NINT_EXTRAPOLATE_WRAP: return launch_one<T, N, false, STRAT, NINT_EXTRAPOLATE_WRAP, true>(P, cfg);
-    case NINT_EXTRAPOLATE_ERROR: return launch_one<T, N, false, STRAT, NINT_EXTRAPOLATE_ERROR, true>(P, cfg);
-    default: return cudaErrorInvalidValue;
-    }
+cudaError_t dispatch_smem(const Params<T>& P, const LaunchCfg& cfg) {
+    return cfg.smem_axes ? launch_one<T, N, false, STRAT, true>(P, cfg) : launch_one<T, N, false, STRAT, false>(P, cfg);
 }
 
 template <class T, int N>
 cudaError_t dispatch_strategy(const Params<T>& P, const LaunchCfg& cfg) {
     switch (cfg.strategy) {
-    case NINT_LINEAR: return dispatch_extrap<T, N, NINT_LINEAR>(P, cfg);
-    case NINT_NEAREST: return dispatch_extrap<T, N, NINT_NEAREST>(P, cfg);
+    case NINT_LINEAR: return dispatch_smem<T, N, NINT_LINEAR>(P, cfg);
+    case NINT_NEAREST: return dispatch_smem<T, N, NINT_NEAREST>(P, cfg);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -38,13 +27,24 @@ template <>
 cudaError_t launch_fixed<NINT_T>(const Params<NINT_T>& P, const LaunchCfg& cfg) {
     switch (cfg.ndim) {
     case 1:
-        if (cfg.strategy == NINT_LEFT_NEAREST) return dispatch_extrap<NINT_T, 1, NINT_LEFT_NEAREST>(P, cfg);
-        if (cfg.strategy == NINT_RIGHT_NEAREST) return dispatch_extrap<NINT_T, 1, NINT_RIGHT_NEAREST>(P, cfg);
+        if (cfg.strategy == NINT_LEFT_NEAREST) return dispatch_smem<NINT_T, 1, NINT_LEFT_NEAREST>(P, cfg);
+        if (cfg.strategy == NINT_RIGHT_NEAREST) return dispatch_smem<NINT_T, 1, NINT_RIGHT_NEAREST>(P, cfg);
         return dispatch_strategy<NINT_T, 1>(P, cfg);
     case 2: return dispatch_strategy<NINT_T, 2>(P, cfg);
     case 3: return dispatch_strategy<NINT_T, 3>(P, cfg);
     default: return cudaErrorInvalidValue;
     }
+}
+
+template <>
+cudaError_t launch_pack_cells<NINT_T>(const Params<NINT_T>& P, int ndim, NINT_T* out, unsigned long long total,
+                                      int sm_count, void* stream) {
+    if (total == 0) return cudaSuccess;
+    const unsigned long long want = (total + kBlock - 1) / kBlock;
+    const unsigned long long cap = (unsigned long long)sm_count * 8ull;
+    pack_cells_kernel<NINT_T><<<(unsigned)(want < cap ? want : cap), kBlock, 0, (cudaStream_t)stream>>>(P.values, out, ndim, P, total);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
 }
 
 template <>

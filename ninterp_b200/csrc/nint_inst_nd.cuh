@@ -8,12 +8,12 @@ namespace {
 template <class T, int N>
 cudaError_t dispatch_nd(const Params<T>& P, const LaunchCfg& cfg) {
     if (cfg.strategy == NINT_LINEAR) {
-        return cfg.smem_axes ? launch_one<T, N, true, NINT_LINEAR, kExtrapRuntime, true>(P, cfg)
-                             : launch_one<T, N, true, NINT_LINEAR, kExtrapRuntime, false>(P, cfg);
+        return cfg.smem_axes ? launch_one<T, N, true, NINT_LINEAR, true>(P, cfg)
+                             : launch_one<T, N, true, NINT_LINEAR, false>(P, cfg);
     }
     if (cfg.strategy == NINT_NEAREST) {
-        return cfg.smem_axes ? launch_one<T, N, true, NINT_NEAREST, kExtrapRuntime, true>(P, cfg)
-                             : launch_one<T, N, true, NINT_NEAREST, kExtrapRuntime, false>(P, cfg);
+        return cfg.smem_axes ? launch_one<T, N, true, NINT_NEAREST, true>(P, cfg)
+                             : launch_one<T, N, true, NINT_NEAREST, false>(P, cfg);
     }
     return cudaErrorInvalidValue;
 }

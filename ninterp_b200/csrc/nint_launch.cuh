@@ -8,9 +8,9 @@ namespace nint {
 
 extern std::atomic<unsigned long long> g_launch_count;
 
-template <class T, int N, bool IS_ND, int STRAT, int EXTRAP, bool SMEM>
-cudaError_t launch_one(const Params<T>& P, const LaunchCfg& cfg) {
-    auto kern = interp_kernel<T, N, IS_ND, STRAT, EXTRAP, SMEM>;
+template <class T, int N, bool IS_ND, int STRAT, bool SMEM, bool CLAMP>
+cudaError_t launch_variant(const Params<T>& P, const LaunchCfg& cfg) {
+    auto kern = interp_kernel<T, N, IS_ND, STRAT, SMEM, CLAMP>;
     const unsigned smem = SMEM ? cfg.smem_bytes : 0u;
     if (smem > 48u * 1024u) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -34,6 +34,13 @@ cudaError_t launch_one(const Params<T>& P, const LaunchCfg& cfg) {
     kern<<<grid, kBlock, smem, (cudaStream_t)cfg.stream>>>(P);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
+}
+
+// Extrapolate::Clamp is folded into the fast path (clamp first, then bracket), so it selects its own kernel.
+template <class T, int N, bool IS_ND, int STRAT, bool SMEM>
+cudaError_t launch_one(const Params<T>& P, const LaunchCfg& cfg) {
+    return (P.extrap == NINT_EXTRAPOLATE_CLAMP) ? launch_variant<T, N, IS_ND, STRAT, SMEM, true>(P, cfg)
+                                                : launch_variant<T, N, IS_ND, STRAT, SMEM, false>(P, cfg);
 }
 
 }  // namespace nint

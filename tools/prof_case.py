@@ -23,16 +23,17 @@ def main():
     ap.add_argument("--points", type=float, default=1e8)
     ap.add_argument("--launches", type=int, default=3)
     ap.add_argument("--status", action="store_true")
+    ap.add_argument("--grid", type=int, default=256)
     a = ap.parse_args()
     n = int(a.points)
     dev = torch.device("cuda", 0)
     rng = np.random.default_rng(0)
     if a.case in ("random", "sorted", "nonuniform"):
-        axes, values = bench.grid_and_values(uniform=a.case != "nonuniform")
+        axes, values = bench.grid_and_values(uniform=a.case != "nonuniform", GRID=a.grid)
         g = nb.Interp3D(*axes, values, nb.strategy.Linear, nb.Extrapolate.Error)
         cols = bench.gen_random(torch, n, dev, seed=1)
         if a.case == "sorted":
-            bench.fill_cell_sorted(torch, cols, dev, seed=2)
+            bench.fill_cell_sorted(torch, cols, dev, seed=2, GRID=a.grid)
         tdt = torch.float64
     elif a.case == "nd5":
         axes = [np.cumsum(rng.uniform(0.5, 1.5, 32)).astype(np.float32) for _ in range(5)]
