@@ -31,7 +31,10 @@
 namespace nint {
 
 constexpr int kMaxDim = NINT_MAX_NDIM;
-constexpr int kBlock = 256;
+#ifndef NINT_BLOCK
+#define NINT_BLOCK 256
+#endif
+constexpr int kBlock = NINT_BLOCK;
 
 // per-axis flags (Params::flags)
 constexpr int kAxisUniform = 1;  // nodes are evenly spaced to within a small fraction of a cell
@@ -507,26 +510,19 @@ __device__ __noinline__ Outcome<T> general_point(const Params<T>& P, const unsig
 }
 
 // Extrapolate::Wrap applied to every axis (three/mod.rs:215-224); out of line because of fmod.
-// Sets *oob when at least one coordinate is outside its axis (the condition for wrapping at all).
 template <class T, int N>
-__device__ __noinline__ Point<T, N> wrap_point(const Params<T>& P, Point<T, N> q, bool* oob) {
-    bool any = false;
+__device__ __noinline__ Point<T, N> wrap_point(const Params<T>& P, Point<T, N> q) {
     Point<T, N> w;
 #pragma unroll
-    for (int d = 0; d < N; ++d) {
-        any = any || !(P.g0[d] <= q.v[d] && q.v[d] <= P.gl[d]);
-        w.v[d] = wrap_coord(q.v[d], P.g0[d], P.gl[d]);
-    }
-    *oob = any;
+    for (int d = 0; d < N; ++d) w.v[d] = wrap_coord(q.v[d], P.g0[d], P.gl[d]);
     return w;
 }
 
-// Fast bracket of one axis: guess the cell, load its two nodes, and verify g[k] < p <= g[k+1]
-// (strictly below g[k+1] where an exact node hit must collapse the axis).  A verified cell is the cell
-// the reference picks: find_nearest_index returns the cell to the left of an exact hit, and `== last`
-// maps to L-2, both of which satisfy the same inequality when nodes are strictly increasing.
-template <class T, bool STRICT>
-__device__ __forceinline__ bool locate_fast(const AxisRef<T>& a, T p, int& k, T& G0, T& G1, T& R) {
+// Fast path, phase 1: the cell guess of one axis.  Uniform axes scale the coordinate; the others read a
+// bucket of the table and count the (at most two) nodes below the point.  The guess is only a guess:
+// verify_cell() decides.  Returns false when the axis cannot use the fast path at all.
+template <class T>
+__device__ __forceinline__ bool guess_cell(const AxisRef<T>& a, T p, int& k) {
     bool ok = (a.flags & kAxisFast) != 0;
     if (a.flags & kAxisUniform) {
         k = to_int_sat((p - a.g0) * a.inv_h);
@@ -542,24 +538,107 @@ __device__ __forceinline__ bool locate_fast(const AxisRef<T>& a, T p, int& k, T&
         k = lo + (n0 < p ? 1 : 0) + (n1 < p ? 1 : 0) - 1;
     }
     k = max(0, min(k, a.L - 2));
+    return ok;
+}
+
+// Fast path, phase 3: g[k] < p <= g[k+1] (strictly below g[k+1] where an exact node hit must collapse the
+// axis).  A verified cell is the cell the reference picks: find_nearest_index returns the cell to the left
+// of an exact hit and maps `== last` to L-2, both of which satisfy the same inequality when the nodes are
+// strictly increasing; and it implies that p is in range and not NaN.
+template <class T, bool STRICT>
+__device__ __forceinline__ bool verify_cell(const AxisRef<T>& a, T p, int k, T& G0, T& G1, T& R) {
     ld_rec(a.rec + 2 * k, G0, R);
     G1 = a.g(k + 1);
-    return ok && (G0 < p) && (STRICT ? (p < G1) : (p <= G1));
+    return (G0 < p) && (STRICT ? (p < G1) : (p <= G1));
 }
 
+// The whole fast path for one point; false when anything about it needs the general path.
+template <class T, int N, bool IS_ND, int STRAT>
+__device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned char* pack, unsigned long long pol,
+                                           const T (&p)[N], T& result) {
+    constexpr bool kCollapse = IS_ND || (N == 1);
+    int k[N];
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < N; ++d) ok = guess_cell<T>(load_axis<T>(P, pack, d), p[d], k[d]) && ok;
+    if (!ok) return false;  // also keeps the speculative loads below inside the table (every axis has >= 2 nodes)
+
+    if (STRAT == NINT_LINEAR) {
+        // start the table loads on the guessed cell, then verify and compute the weights under their latency
+        T cube[1 << N];
+        if (P.cells != nullptr) {
+            long long cell = 0;
+#pragma unroll
+            for (int d = 0; d < N; ++d) cell += (long long)k[d] * P.cstride[d];
+            ld_cells<(1 << N)>(P.cells + cell * (1 << N), cube);
+        } else {
+            long long base = 0;
+            long long step[N];
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                base += (long long)k[d] * P.vstride[d];
+                step[d] = P.vstride[d];
+            }
+            gather_rows<T, N>(P.values + base, step, pol, false, cube);
+        }
+        T t[N];
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            T G0, G1, r;
+            ok = verify_cell<T, kCollapse>(load_axis<T>(P, pack, d), p[d], k[d], G0, G1, r) && ok;
+            const T a = p[d] - G0;
+            ok = ok && in_div_window(a) && (r != T(0));
+            t[d] = div_markstein<T>(a, G1 - G0, r);
+        }
+        // reduce axis 0 first, then 1, ...: v_l * (1 - t) + v_u * t, each op rounded separately
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            const int half = 1 << (N - 1 - d);
+            const T td = t[d];
+            const T sd = T(1) - td;
+#pragma unroll
+            for (int j = 0; j < half; ++j) cube[j] = cube[j] * sd + cube[half + j] * td;
+        }
+        result = cube[0];
+        return ok;
+    } else {
+        long long off = 0;
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            T G0, G1, r;
+            ok = verify_cell<T, kCollapse>(load_axis<T>(P, pack, d), p[d], k[d], G0, G1, r) && ok;
+            int idx = k[d];
+            if (STRAT == NINT_NEAREST) idx += ((p[d] - G0) < (G1 - p[d])) ? 0 : 1;  // tie -> upper (three/strategies.rs:70-74)
+            if (STRAT == NINT_RIGHT_NEAREST) idx += 1;
+            off += (long long)idx * P.vstride[d];
+        }
+        result = ld_table(P.values + off, pol);  // idx <= L-1 on every axis: inside the table even if !ok
+        return ok;
+    }
+}
+
+// How the Extrapolate policy enters the fast path (kernel template argument).
+constexpr int kPrePlain = 0;  // nothing to do up front (Error, Fill, Enable: out-of-range points take the general path)
+constexpr int kPreClamp = 1;  // Clamp: clamp every coordinate first, then bracket
+constexpr int kPreWrap = 2;   // Wrap: points that fail the fast path are wrapped (if out of range) and retried
+
 // ---------------------------------------------------------------------------------------------
-// The kernel: persistent CTAs, grid-stride over the batch, one point per thread per trip.
+// The kernel: persistent CTAs, grid-stride over the batch, one point per thread per trip, the next
+// trip's coordinates prefetched while the current point is evaluated.
 // ---------------------------------------------------------------------------------------------
-// Resident CTAs per SM the register allocator must leave room for: the fast path of the low-dimensional
-// kernels fits 64 registers (4 CTAs of 256 threads); the out-of-line general path may spill instead.
-#ifndef NINT_MIN_CTAS
-#define NINT_MIN_CTAS 4
-#endif
+// Resident CTAs per SM the register allocator must leave room for.  Measured on B200 (tools/exp_ctas.sh):
+// the 3-D f64 kernel is fastest with 80 registers (3 CTAs of 256 threads); 64 registers spill the prefetched
+// coordinates, 128 leave too few warps to hide the table-load latency.  NINT_MIN_CTAS overrides for tuning.
 constexpr int min_ctas(int n, int elem_bytes) {
-    return (n <= 3) ? NINT_MIN_CTAS : ((n == 4 || (n == 5 && elem_bytes == 4)) ? 2 : 1);
+#ifdef NINT_MIN_CTAS
+    if (n <= 3) return NINT_MIN_CTAS;
+#endif
+    if (n <= 2) return 4;
+    if (n == 3) return elem_bytes == 8 ? 3 : 4;
+    return (n == 4 || (n == 5 && elem_bytes == 4)) ? 2 : 1;
 }
 
-template <class T, int N, bool IS_ND, int STRAT, bool SMEM, bool CLAMP>
+template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE>
 __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_kernel(const __grid_constant__ Params<T> P) {
     extern __shared__ __align__(16) unsigned char smem_pack[];
     const unsigned char* pack;
@@ -567,13 +646,10 @@ __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_ke
         const uint4* src = reinterpret_cast<const uint4*>(P.pack);
         uint4* dst = reinterpret_cast<uint4*>(smem_pack);
         for (unsigned i = threadIdx.x; i < P.pack_bytes / 16u; i += blockDim.x) dst[i] = __ldg(src + i);
-        __syncthreads();
         pack = smem_pack;
     } else {
         pack = P.pack;
     }
-
-    constexpr bool kCollapse = IS_ND || (N == 1);
     const unsigned long long pol = make_table_policy(P.l2_frac);
 
     // per-CTA failure counters live in shared memory (failures are the rare case; no registers held)
@@ -582,84 +658,42 @@ __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_ke
     __syncthreads();
 
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-        Point<T, N> q;
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    Point<T, N> q;
+    if (i < P.n) {
 #pragma unroll
         for (int d = 0; d < N; ++d) q.v[d] = ld_stream(P.coords[d] + i * P.coord_stride);
+    }
+    for (; i < P.n; i += stride) {
+        // prefetch the next trip's coordinates
+        Point<T, N> qn = q;
+        const unsigned long long in = i + stride;
+        if (in < P.n) {
+#pragma unroll
+            for (int d = 0; d < N; ++d) qn.v[d] = ld_stream(P.coords[d] + in * P.coord_stride);
+        }
 
-        // ---- fast path: bracket every axis, verified against the nodes.  Under Extrapolate::Wrap a point
-        // that fails is wrapped (if it is out of range) and gets one more attempt before the general path.
+        T p[N];
+        bool oob = false;
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            // Clamp touches every axis as soon as one is out of range and leaves in-range coordinates
+            // alone, so clamping up front is the same map (three/mod.rs:205-214)
+            p[d] = (PRE == kPreClamp) ? clamp_coord(q.v[d], P.g0[d], P.gl[d]) : q.v[d];
+            if (PRE == kPreWrap) oob = oob || !(P.g0[d] <= q.v[d] && q.v[d] <= P.gl[d]);
+        }
+        if (PRE == kPreWrap) {
+            // Wrap re-maps every axis as soon as one coordinate is out of range (three/mod.rs:215-224)
+            if (oob) {
+                const Point<T, N> w = wrap_point<T, N>(P, q);
+#pragma unroll
+                for (int d = 0; d < N; ++d) p[d] = w.v[d];
+            }
+        }
         unsigned status = NINT_STATUS_OK;
         T result;
-        Point<T, N> pt = q;
-        bool retried = false;
-        for (;;) {
-            int k[N];
-            T t[N];
-            bool ok = true;
-#pragma unroll
-            for (int d = 0; d < N; ++d) {
-                const AxisRef<T> ax = load_axis<T>(P, pack, d);
-                // Clamp touches every axis as soon as one is out of range and leaves in-range coordinates
-                // alone, so clamping up front is the same map (three/mod.rs:205-214)
-                const T p = CLAMP ? clamp_coord(pt.v[d], ax.g0, ax.gl) : pt.v[d];
-                T G0, G1, r;
-                ok = locate_fast<T, kCollapse>(ax, p, k[d], G0, G1, r) && ok;
-                t[d] = T(0);
-                if (STRAT == NINT_LINEAR) {
-                    const T a = p - G0;
-                    ok = ok && in_div_window(a) && (r != T(0));
-                    t[d] = div_markstein<T>(a, G1 - G0, r);
-                } else if (STRAT == NINT_NEAREST) {
-                    k[d] += ((p - G0) < (G1 - p)) ? 0 : 1;  // tie -> upper (three/strategies.rs:70-74)
-                } else if (STRAT == NINT_RIGHT_NEAREST) {
-                    k[d] += 1;
-                }
-            }
-            if (ok) {
-                if (STRAT == NINT_LINEAR) {
-                    T cube[1 << N];
-                    if (P.cells != nullptr) {
-                        long long cell = 0;
-#pragma unroll
-                        for (int d = 0; d < N; ++d) cell += (long long)k[d] * P.cstride[d];
-                        ld_cells<(1 << N)>(P.cells + cell * (1 << N), cube);
-                    } else {
-                        long long base = 0;
-                        long long step[N];
-#pragma unroll
-                        for (int d = 0; d < N; ++d) {
-                            base += (long long)k[d] * P.vstride[d];
-                            step[d] = P.vstride[d];
-                        }
-                        gather_rows<T, N>(P.values + base, step, pol, false, cube);
-                    }
-#pragma unroll
-                    for (int d = 0; d < N; ++d) {
-                        const int half = 1 << (N - 1 - d);
-                        const T td = t[d];
-                        const T sd = T(1) - td;
-#pragma unroll
-                        for (int j = 0; j < half; ++j) cube[j] = cube[j] * sd + cube[half + j] * td;
-                    }
-                    result = cube[0];
-                } else {
-                    long long off = 0;
-#pragma unroll
-                    for (int d = 0; d < N; ++d) off += (long long)k[d] * P.vstride[d];
-                    result = ld_table(P.values + off, pol);
-                }
-                break;
-            }
-            if (!retried && P.extrap == NINT_EXTRAPOLATE_WRAP) {
-                retried = true;
-                bool oob;
-                const Point<T, N> w = wrap_point<T, N>(P, q, &oob);
-                if (oob) {
-                    pt = w;
-                    continue;
-                }
-            }
+        const bool ok = fast_point<T, N, IS_ND, STRAT>(P, pack, pol, p, result);
+        if (!ok) {
             const Outcome<T> o = general_point<T, N, IS_ND, STRAT>(P, pack, q);
             result = o.value;
             status = o.status;
@@ -669,10 +703,10 @@ __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_ke
                 atomicAdd(&s_info[slot], 1ull);
                 atomicMin(&s_info[2 + slot], i + P.index_base);
             }
-            break;
         }
         st_stream(P.out + i, result);
         if (P.status) P.status[i] = (uint8_t)status;
+        q = qn;
     }
 
     if (P.info) {

@@ -8,9 +8,9 @@ namespace nint {
 
 extern std::atomic<unsigned long long> g_launch_count;
 
-template <class T, int N, bool IS_ND, int STRAT, bool SMEM, bool CLAMP>
+template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE>
 cudaError_t launch_variant(const Params<T>& P, const LaunchCfg& cfg) {
-    auto kern = interp_kernel<T, N, IS_ND, STRAT, SMEM, CLAMP>;
+    auto kern = interp_kernel<T, N, IS_ND, STRAT, SMEM, PRE>;
     const unsigned smem = SMEM ? cfg.smem_bytes : 0u;
     if (smem > 48u * 1024u) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -36,11 +36,12 @@ cudaError_t launch_variant(const Params<T>& P, const LaunchCfg& cfg) {
     return cudaGetLastError();
 }
 
-// Extrapolate::Clamp is folded into the fast path (clamp first, then bracket), so it selects its own kernel.
+// Clamp and Wrap enter the fast path (clamp first / wrap and retry), so they select their own kernels.
 template <class T, int N, bool IS_ND, int STRAT, bool SMEM>
 cudaError_t launch_one(const Params<T>& P, const LaunchCfg& cfg) {
-    return (P.extrap == NINT_EXTRAPOLATE_CLAMP) ? launch_variant<T, N, IS_ND, STRAT, SMEM, true>(P, cfg)
-                                                : launch_variant<T, N, IS_ND, STRAT, SMEM, false>(P, cfg);
+    if (P.extrap == NINT_EXTRAPOLATE_CLAMP) return launch_variant<T, N, IS_ND, STRAT, SMEM, kPreClamp>(P, cfg);
+    if (P.extrap == NINT_EXTRAPOLATE_WRAP) return launch_variant<T, N, IS_ND, STRAT, SMEM, kPreWrap>(P, cfg);
+    return launch_variant<T, N, IS_ND, STRAT, SMEM, kPrePlain>(P, cfg);
 }
 
 }  // namespace nint
