@@ -215,8 +215,17 @@ void classify_axis(const nint_handle* h, int d, AxisMeta& a) {
     a.L = L;
     a.g0 = load_elem(h->dtype, nodes, 0);
     a.gl = load_elem(h->dtype, nodes, L - 1);
+    // strictly increasing, and every cell width inside the window for which a reciprocal is stored
     bool strict = L >= 2;
-    for (int i = 0; i + 1 < L && strict; ++i) strict = load_elem(h->dtype, nodes, i) < load_elem(h->dtype, nodes, i + 1);
+    for (int i = 0; i + 1 < L && strict; ++i) {
+        if (h->dtype == NINT_F64) {
+            const double w = ((const double*)nodes)[i + 1] - ((const double*)nodes)[i];
+            strict = (w >= 0x1p-500 && w < 0x1p500);
+        } else {
+            const float w = ((const float*)nodes)[i + 1] - ((const float*)nodes)[i];
+            strict = (w >= 0x1p-60f && w < 0x1p60f);
+        }
+    }
     a.flags = strict ? nint::kAxisFast : 0;
     a.inv_h = 0.0;
     const double span = a.gl - a.g0;
@@ -469,6 +478,9 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     cfg.is_nd = h->kind == NINT_KIND_ND;
     cfg.strategy = h->strategy;
     cfg.smem_axes = h->smem_axes;
+    cfg.all_uniform = 1;
+    for (int d = 0; d < h->ndim_eff; ++d)
+        if ((h->ax[d].flags & (nint::kAxisUniform | nint::kAxisFast)) != (nint::kAxisUniform | nint::kAxisFast)) cfg.all_uniform = 0;
     cfg.smem_bytes = h->pack_bytes;
     cfg.sm_count = h->sm_count;
     cfg.stream = stream;

@@ -34,11 +34,16 @@ constexpr int kMaxDim = NINT_MAX_NDIM;
 #ifndef NINT_BLOCK
 #define NINT_BLOCK 256
 #endif
+#ifndef NINT_UNROLL
+#define NINT_UNROLL 1  // trips of the point loop unrolled together (tuning knob; measured: see tools/exp_ctas.sh)
+#endif
 constexpr int kBlock = NINT_BLOCK;
+constexpr int kUnroll = NINT_UNROLL;
 
 // per-axis flags (Params::flags)
 constexpr int kAxisUniform = 1;  // nodes are evenly spaced to within a small fraction of a cell
-constexpr int kAxisFast = 2;     // axis may use the fast path (>= 2 nodes, strictly increasing)
+constexpr int kAxisFast = 2;     // axis may use the fast path: >= 2 nodes, strictly increasing, every cell
+                                 // width inside the division window (all reciprocals stored)
 
 template <class T>
 struct Params {
@@ -250,7 +255,10 @@ __device__ __forceinline__ float div_markstein<float>(float a, float w, float r)
     return __fmaf_rn(e, r, q);
 }
 // |a| in [2^-500, 2^500) for f64, [2^-60, 2^60) for f32: with w in the same window (host side, r != 0)
-// every intermediate of div_markstein() stays normal.
+// every intermediate of div_markstein() stays normal.  in_div_window_pos() is the same test for an `a`
+// already known to satisfy 0 < a <= w with w inside the window: only the lower bound can fail.
+__device__ __forceinline__ bool in_div_window_pos(double a) { return __double2hiint(a) >= 0x20b00000; }
+__device__ __forceinline__ bool in_div_window_pos(float a) { return __float_as_int(a) >= 0x21800000; }
 __device__ __forceinline__ bool in_div_window(double a) {
     const unsigned hi = (unsigned)__double2hiint(a) & 0x7fffffffu;
     return (hi - 0x20b00000u) < 0x3e800000u;
@@ -521,8 +529,14 @@ __device__ __noinline__ Point<T, N> wrap_point(const Params<T>& P, Point<T, N> q
 // Fast path, phase 1: the cell guess of one axis.  Uniform axes scale the coordinate; the others read a
 // bucket of the table and count the (at most two) nodes below the point.  The guess is only a guess:
 // verify_cell() decides.  Returns false when the axis cannot use the fast path at all.
-template <class T>
+template <class T, bool UNI>
 __device__ __forceinline__ bool guess_cell(const AxisRef<T>& a, T p, int& k) {
+    if (UNI) {
+        // kernel variant for interpolators whose axes are all uniform and fast-path eligible
+        k = to_int_sat((p - a.g0) * a.inv_h);
+        k = max(0, min(k, a.L - 2));
+        return true;
+    }
     bool ok = (a.flags & kAxisFast) != 0;
     if (a.flags & kAxisUniform) {
         k = to_int_sat((p - a.g0) * a.inv_h);
@@ -553,18 +567,34 @@ __device__ __forceinline__ bool verify_cell(const AxisRef<T>& a, T p, int k, T& 
 }
 
 // The whole fast path for one point; false when anything about it needs the general path.
-template <class T, int N, bool IS_ND, int STRAT>
+template <class T, int N, bool IS_ND, int STRAT, bool UNI>
 __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned char* pack, unsigned long long pol,
                                            const T (&p)[N], T& result) {
     constexpr bool kCollapse = IS_ND || (N == 1);
     int k[N];
     bool ok = true;
 #pragma unroll
-    for (int d = 0; d < N; ++d) ok = guess_cell<T>(load_axis<T>(P, pack, d), p[d], k[d]) && ok;
+    for (int d = 0; d < N; ++d) ok = guess_cell<T, UNI>(load_axis<T>(P, pack, d), p[d], k[d]) && ok;
     if (!ok) return false;  // also keeps the speculative loads below inside the table (every axis has >= 2 nodes)
 
     if (STRAT == NINT_LINEAR) {
-        // start the table loads on the guessed cell, then verify and compute the weights under their latency
+        // Verify and compute the weights first, then gather and blend: keeping the 2^N corner registers out of
+        // the weight computation lets the 3-D f64 kernel fit 64 registers (4 CTAs/SM), and on B200 the extra
+        // resident warps hide the table-load latency better than issuing the loads early does (measured).
+        T t[N];
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            T G0, G1, r;
+            ok = verify_cell<T, kCollapse>(load_axis<T>(P, pack, d), p[d], k[d], G0, G1, r) && ok;
+            // kAxisFast guarantees every cell of the axis has a stored reciprocal (width inside the window),
+            // and the verified bracket gives 0 < a <= w: only a tiny `a` can leave the window
+            const T a = p[d] - G0;
+            ok = ok && in_div_window_pos(a);
+            t[d] = div_markstein<T>(a, G1 - G0, r);
+        }
+#ifndef NINT_EARLY_OUT
+        if (!ok) return false;
+#endif
         T cube[1 << N];
         if (P.cells != nullptr) {
             long long cell = 0;
@@ -580,15 +610,6 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
                 step[d] = P.vstride[d];
             }
             gather_rows<T, N>(P.values + base, step, pol, false, cube);
-        }
-        T t[N];
-#pragma unroll
-        for (int d = 0; d < N; ++d) {
-            T G0, G1, r;
-            ok = verify_cell<T, kCollapse>(load_axis<T>(P, pack, d), p[d], k[d], G0, G1, r) && ok;
-            const T a = p[d] - G0;
-            ok = ok && in_div_window(a) && (r != T(0));
-            t[d] = div_markstein<T>(a, G1 - G0, r);
         }
         // reduce axis 0 first, then 1, ...: v_l * (1 - t) + v_u * t, each op rounded separately
 #pragma unroll
@@ -634,11 +655,11 @@ constexpr int min_ctas(int n, int elem_bytes) {
     if (n <= 3) return NINT_MIN_CTAS;
 #endif
     if (n <= 2) return 4;
-    if (n == 3) return elem_bytes == 8 ? 3 : 4;
+    if (n == 3) return 4;
     return (n == 4 || (n == 5 && elem_bytes == 4)) ? 2 : 1;
 }
 
-template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE>
+template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE, bool UNI>
 __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_kernel(const __grid_constant__ Params<T> P) {
     extern __shared__ __align__(16) unsigned char smem_pack[];
     const unsigned char* pack;
@@ -664,6 +685,7 @@ __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_ke
 #pragma unroll
         for (int d = 0; d < N; ++d) q.v[d] = ld_stream(P.coords[d] + i * P.coord_stride);
     }
+#pragma unroll kUnroll
     for (; i < P.n; i += stride) {
         // prefetch the next trip's coordinates
         Point<T, N> qn = q;
@@ -692,7 +714,7 @@ __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_ke
         }
         unsigned status = NINT_STATUS_OK;
         T result;
-        const bool ok = fast_point<T, N, IS_ND, STRAT>(P, pack, pol, p, result);
+        const bool ok = fast_point<T, N, IS_ND, STRAT, UNI>(P, pack, pol, p, result);
         if (!ok) {
             const Outcome<T> o = general_point<T, N, IS_ND, STRAT>(P, pack, q);
             result = o.value;
@@ -762,6 +784,7 @@ struct LaunchCfg {
     int is_nd;
     int strategy;
     int smem_axes;  // stage the axis pack in shared memory
+    int all_uniform;  // every axis is uniform and fast-path eligible
     unsigned smem_bytes;
     int sm_count;
     void* stream;

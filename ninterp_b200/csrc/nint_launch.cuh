@@ -8,9 +8,9 @@ namespace nint {
 
 extern std::atomic<unsigned long long> g_launch_count;
 
-template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE>
+template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE, bool UNI>
 cudaError_t launch_variant(const Params<T>& P, const LaunchCfg& cfg) {
-    auto kern = interp_kernel<T, N, IS_ND, STRAT, SMEM, PRE>;
+    auto kern = interp_kernel<T, N, IS_ND, STRAT, SMEM, PRE, UNI>;
     const unsigned smem = SMEM ? cfg.smem_bytes : 0u;
     if (smem > 48u * 1024u) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -36,12 +36,18 @@ cudaError_t launch_variant(const Params<T>& P, const LaunchCfg& cfg) {
     return cudaGetLastError();
 }
 
-// Clamp and Wrap enter the fast path (clamp first / wrap and retry), so they select their own kernels.
+// Clamp and Wrap enter the fast path (clamp first / wrap and retry), so they select their own kernels; so do
+// interpolators whose axes are all uniform (no bucket tables, no per-axis flags in the point loop).
+template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE>
+cudaError_t launch_uni(const Params<T>& P, const LaunchCfg& cfg) {
+    if (SMEM && cfg.all_uniform) return launch_variant<T, N, IS_ND, STRAT, SMEM, PRE, SMEM>(P, cfg);
+    return launch_variant<T, N, IS_ND, STRAT, SMEM, PRE, false>(P, cfg);
+}
 template <class T, int N, bool IS_ND, int STRAT, bool SMEM>
 cudaError_t launch_one(const Params<T>& P, const LaunchCfg& cfg) {
-    if (P.extrap == NINT_EXTRAPOLATE_CLAMP) return launch_variant<T, N, IS_ND, STRAT, SMEM, kPreClamp>(P, cfg);
-    if (P.extrap == NINT_EXTRAPOLATE_WRAP) return launch_variant<T, N, IS_ND, STRAT, SMEM, kPreWrap>(P, cfg);
-    return launch_variant<T, N, IS_ND, STRAT, SMEM, kPrePlain>(P, cfg);
+    if (P.extrap == NINT_EXTRAPOLATE_CLAMP) return launch_uni<T, N, IS_ND, STRAT, SMEM, kPreClamp>(P, cfg);
+    if (P.extrap == NINT_EXTRAPOLATE_WRAP) return launch_uni<T, N, IS_ND, STRAT, SMEM, kPreWrap>(P, cfg);
+    return launch_uni<T, N, IS_ND, STRAT, SMEM, kPrePlain>(P, cfg);
 }
 
 }  // namespace nint
