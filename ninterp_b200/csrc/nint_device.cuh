@@ -592,9 +592,6 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
             ok = ok && in_div_window_pos(a);
             t[d] = div_markstein<T>(a, G1 - G0, r);
         }
-#ifndef NINT_EARLY_OUT
-        if (!ok) return false;
-#endif
         T cube[1 << N];
         if (P.cells != nullptr) {
             long long cell = 0;
@@ -648,8 +645,9 @@ constexpr int kPreWrap = 2;   // Wrap: points that fail the fast path are wrappe
 // trip's coordinates prefetched while the current point is evaluated.
 // ---------------------------------------------------------------------------------------------
 // Resident CTAs per SM the register allocator must leave room for.  Measured on B200 (tools/exp_ctas.sh):
-// the 3-D f64 kernel is fastest with 80 registers (3 CTAs of 256 threads); 64 registers spill the prefetched
-// coordinates, 128 leave too few warps to hide the table-load latency.  NINT_MIN_CTAS overrides for tuning.
+// with the weights computed before the table loads the 3-D f64 fast path fits 64 registers, and 4 CTAs of 256
+// threads (32 warps/SM) beat 3 CTAs at 80 registers (136 vs 115 Gpoints/s on cell-ordered queries); 128
+// registers leave too few warps to hide the table-load latency.  NINT_MIN_CTAS overrides for tuning.
 constexpr int min_ctas(int n, int elem_bytes) {
 #ifdef NINT_MIN_CTAS
     if (n <= 3) return NINT_MIN_CTAS;
