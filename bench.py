@@ -139,7 +139,7 @@ def run_reference(args, rank):
     import oracle_binding as O
 
     axes, values = grid_and_values()
-    threads = O.max_threads()
+    threads = host_threads(O)
     o = O.Oracle(axes, values, O.LINEAR, O.ERROR)
     rng = np.random.default_rng(99)
     # calibrate, then size the per-step sample so the whole run stays within ~2 minutes
@@ -169,6 +169,14 @@ def run_reference(args, rank):
         "host_cpu": _cpu_model(),
     }
     print(json.dumps(line), flush=True)
+
+
+def host_threads(O):
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what the CPU arm wants)."""
+    try:
+        return max(O.max_threads(), len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(O.max_threads(), os.cpu_count() or 1)
 
 
 def _cpu_model():
@@ -385,7 +393,7 @@ def run_cpu_baseline(axes, values, sample_cols, sample_out, target_seconds):
     sys.path.insert(0, str(ROOT / "tests"))
     import oracle_binding as O
 
-    threads = O.max_threads()
+    threads = host_threads(O)
     o = O.Oracle(axes, values, O.LINEAR, O.ERROR)
     cal_n = min(2_000_000, len(sample_cols[0]))
     t0 = time.perf_counter()

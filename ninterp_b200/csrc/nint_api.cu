@@ -284,7 +284,7 @@ int build_pack(nint_handle* h) {
     for (int d = 0; d < n; ++d) {
         AxisMeta& a = h->ax[d];
         const bool uniform = (a.flags & nint::kAxisUniform) != 0;
-        double per_cell = uniform ? 1.0 : 2.0;
+        double per_cell = uniform ? 1.0 / 8 : 2.0;  // uniform axes: only the (rare) general path searches
         // shrink first if even the starting table does not fit
         while (per_cell > 1.0 / 64 && rec_bytes + lut_bytes + (unsigned long long)(per_cell * a.L) * 8 > budget) per_cell *= 0.5;
         double wide = make_buckets(h, d, per_cell, a, luts[d]);
@@ -400,7 +400,7 @@ int build_cells(nint_handle* h) {
     const unsigned long long bytes = total * es;
     size_t free_b = 0, total_b = 0;
     NINT_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    if (bytes > free_b / 4 || n > 6) return NINT_OK;
+    if (bytes > free_b / 4 || n > 6 || cells >= (1ull << 31)) return NINT_OK;
     long long stride = 1;
     for (int d = n - 1; d >= 0; --d) {
         h->ax[d].cstride = stride;

@@ -566,6 +566,24 @@ __device__ __forceinline__ bool verify_cell(const AxisRef<T>& a, T p, int k, T& 
     return (G0 < p) && (STRICT ? (p < G1) : (p <= G1));
 }
 
+// Verification for Linear plus the division-window test on a = p - g[k].  Besides g[k] < p <= g[k+1] the
+// hard-coded interpolators also accept the in-range point p == g[0] in the first cell, for which the reference
+// computes t = 0/w = +0 (three/strategies.rs:16-27) -- div_markstein(0, w, r) returns exactly that.  Where axes
+// collapse, an exact hit selects the node instead and is left to the general path.
+// kAxisFast guarantees every cell has a stored reciprocal (width inside the window) and the verified bracket
+// gives 0 <= a <= w, so only a tiny non-zero `a` can leave the window.
+template <class T, bool STRICT>
+__device__ __forceinline__ bool verify_cell_linear(const AxisRef<T>& ax, T p, int k, T& a, T& w, T& R) {
+    T G0, G1;
+    ld_rec(ax.rec + 2 * k, G0, R);
+    G1 = ax.g(k + 1);
+    a = p - G0;
+    w = G1 - G0;
+    if (STRICT) return (G0 < p) && (p < G1) && in_div_window_pos(a);
+    const bool first = (k == 0) && (p == G0);
+    return ((G0 < p && in_div_window_pos(a)) || first) && (p <= G1);
+}
+
 // The whole fast path for one point; false when anything about it needs the general path.
 template <class T, int N, bool IS_ND, int STRAT, bool UNI>
 __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned char* pack, unsigned long long pol,
@@ -584,13 +602,9 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
         T t[N];
 #pragma unroll
         for (int d = 0; d < N; ++d) {
-            T G0, G1, r;
-            ok = verify_cell<T, kCollapse>(load_axis<T>(P, pack, d), p[d], k[d], G0, G1, r) && ok;
-            // kAxisFast guarantees every cell of the axis has a stored reciprocal (width inside the window),
-            // and the verified bracket gives 0 < a <= w: only a tiny `a` can leave the window
-            const T a = p[d] - G0;
-            ok = ok && in_div_window_pos(a);
-            t[d] = div_markstein<T>(a, G1 - G0, r);
+            T a, w, r;
+            ok = verify_cell_linear<T, kCollapse>(load_axis<T>(P, pack, d), p[d], k[d], a, w, r) && ok;
+            t[d] = div_markstein<T>(a, w, r);
         }
         T cube[1 << N];
         if (P.cells != nullptr) {
