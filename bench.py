@@ -292,7 +292,7 @@ def run_b200(args, rank, local_rank, world):
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "kernel": "interp_kernel<double,3,fixed,Linear,Error,smem>", "kernel_ms": kernel_ms,
+                "kernel": "interp_kernel<double,3,fixed,Linear,smem,plain,uniform>", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_point": BYTES_PER_POINT, "points_per_launch": n}
 
     # parity sample of the main workload, kept for the cpu_baseline leg
