@@ -155,6 +155,14 @@ NINT_API int nint_interpolate_batch_aos(nint_handle* h, const void* points, size
 NINT_API int nint_interpolate_batch_host(nint_handle* h, int layout, const void* data, size_t n, void* out_host,
                                 uint8_t* status_host, nint_batch_info* info_host);
 
+/* Host-buffer batch sharded over several GPUs of one box: `handles` are nh interpolators built from the same
+ * data on different devices (the grid is replicated); the batch is split into nh contiguous index ranges that
+ * run concurrently, one host thread per device, each through nint_interpolate_batch_host, so the host<->device
+ * copies use every GPU's own PCIe link.  There is no collective: results land in place in out_host.  Indices
+ * in info_host refer to the whole batch.  Return value as for nint_interpolate_batch_host. */
+NINT_API int nint_interpolate_batch_host_multi(nint_handle* const* handles, int nh, int layout, const void* data, size_t n,
+                                               void* out_host, uint8_t* status_host, nint_batch_info* info_host);
+
 /* Interpolator::interpolate(&self, point: &[T]) -> Result<T, InterpolateError> for one point
  * (three/mod.rs:193-238): point_len != ndim gives NINT_E_POINT_LENGTH. */
 NINT_API int nint_interpolate(nint_handle* h, const void* point, size_t point_len, void* out);

@@ -8,9 +8,11 @@ from . import strategy
 from .error import EngineError, InterpolateError, ReferencePanic, ValidateError
 from .extrapolate import Extrapolate
 from .interpolator import Interp0D, Interp1D, Interp2D, Interp3D, InterpND, InterpolatorEnum
+from .multi import ReplicatedInterpolator
+from .serde import from_json, to_json
 
 __all__ = [
     "strategy", "Extrapolate", "Interp0D", "Interp1D", "Interp2D", "Interp3D", "InterpND", "InterpolatorEnum",
-    "ValidateError", "InterpolateError", "ReferencePanic", "EngineError",
+    "ValidateError", "InterpolateError", "ReferencePanic", "EngineError", "ReplicatedInterpolator", "from_json", "to_json",
 ]
 __version__ = "0.1.0"

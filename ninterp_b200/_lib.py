@@ -26,7 +26,7 @@ MAX_NDIM = 8
 # every symbol include/ninterp_cuda.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "nint_create", "nint_destroy", "nint_ndim", "nint_validate", "nint_set_extrapolate", "nint_set_strategy",
-    "nint_interpolate_batch", "nint_interpolate_batch_aos", "nint_interpolate_batch_host", "nint_interpolate",
+    "nint_interpolate_batch", "nint_interpolate_batch_aos", "nint_interpolate_batch_host", "nint_interpolate_batch_host_multi", "nint_interpolate",
     "nint_host_alloc", "nint_host_free", "nint_last_error_message", "nint_last_error_dim", "nint_version",
     "nint_launch_count", "nint_selftest_divide",
 ]
@@ -63,6 +63,7 @@ def lib() -> C.CDLL:
     L.nint_interpolate_batch_aos.argtypes = [vp, vp, sz, vp, vp, vp, vp]
     L.nint_interpolate_batch_host.argtypes = [vp, i32, vp, sz, vp, vp, C.POINTER(BatchInfo)]
     L.nint_interpolate.argtypes = [vp, vp, sz, vp]
+    L.nint_interpolate_batch_host_multi.argtypes = [C.POINTER(vp), i32, i32, vp, sz, vp, vp, C.POINTER(BatchInfo)]
     L.nint_host_alloc.argtypes = [C.POINTER(vp), sz]
     L.nint_host_free.argtypes = [vp]
     L.nint_last_error_message.restype = C.c_char_p

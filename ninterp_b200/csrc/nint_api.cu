@@ -16,6 +16,7 @@
 #include <limits>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "nint_device.cuh"
@@ -821,6 +822,68 @@ int nint_interpolate_batch_host(nint_handle* h, int layout, const void* data, si
         return fail(NINT_E_EXTRAPOLATE, -1,
                     "attempted to interpolate at point beyond grid data: %llu point(s), first at index %llu",
                     (unsigned long long)info.n_error, (unsigned long long)info.first_error);
+    return NINT_OK;
+}
+
+int nint_interpolate_batch_host_multi(nint_handle* const* handles, int nh, int layout, const void* data, size_t n,
+                                      void* out_host, uint8_t* status_host, nint_batch_info* info_host) {
+    if (!handles || nh < 1) return fail(NINT_E_INVALID_ARGUMENT, -1, "no handles");
+    for (int r = 0; r < nh; ++r) {
+        if (!handles[r]) return fail(NINT_E_INVALID_ARGUMENT, -1, "handle %d is NULL", r);
+        if (handles[r]->dtype != handles[0]->dtype || handles[r]->ndim_eff != handles[0]->ndim_eff)
+            return fail(NINT_E_INVALID_ARGUMENT, -1, "handle %d does not match handle 0 (dtype/ndim)", r);
+    }
+    if (nh == 1) return nint_interpolate_batch_host(handles[0], layout, data, n, out_host, status_host, info_host);
+    if (layout != NINT_LAYOUT_SOA && layout != NINT_LAYOUT_AOS)
+        return fail(NINT_E_INVALID_ARGUMENT, -1, "unknown layout %d", layout);
+    const int nd = handles[0]->ndim_eff;
+    const size_t es = elem_size(handles[0]->dtype);
+    std::vector<int> rc(nh, NINT_OK);
+    std::vector<nint_batch_info> info(nh, nint_batch_info{0, 0, UINT64_MAX, UINT64_MAX});
+    std::vector<std::string> msg(nh);
+    std::vector<size_t> lo(nh + 1);
+    for (int r = 0; r <= nh; ++r) lo[r] = (size_t)((unsigned __int128)n * (unsigned)r / (unsigned)nh);
+    std::vector<std::thread> workers;
+    for (int r = 0; r < nh; ++r) {
+        workers.emplace_back([&, r]() {
+            const size_t start = lo[r], m = lo[r + 1] - lo[r];
+            if (m == 0) return;
+            const void* sub = nullptr;
+            const void* cols[NINT_MAX_NDIM] = {};
+            if (layout == NINT_LAYOUT_AOS) {
+                sub = (const unsigned char*)data + start * (size_t)nd * es;
+            } else {
+                for (int d = 0; d < nd; ++d) cols[d] = (const unsigned char*)((const void* const*)data)[d] + start * es;
+                sub = cols;
+            }
+            rc[r] = nint_interpolate_batch_host(handles[r], layout, sub, m, (unsigned char*)out_host + start * es,
+                                                status_host ? status_host + start : nullptr, &info[r]);
+            if (rc[r] != NINT_OK) msg[r] = nint_last_error_message();  // thread-local in the worker
+        });
+    }
+    for (auto& w : workers) w.join();
+    nint_batch_info total{0, 0, UINT64_MAX, UINT64_MAX};
+    int worst = NINT_OK;
+    std::string worst_msg;
+    for (int r = 0; r < nh; ++r) {
+        total.n_error += info[r].n_error;
+        total.n_panic += info[r].n_panic;
+        if (info[r].n_error) total.first_error = std::min<uint64_t>(total.first_error, info[r].first_error + lo[r]);
+        if (info[r].n_panic) total.first_panic = std::min<uint64_t>(total.first_panic, info[r].first_panic + lo[r]);
+        if (rc[r] != NINT_OK && rc[r] != NINT_E_EXTRAPOLATE && rc[r] != NINT_E_PANIC && worst == NINT_OK) {
+            worst = rc[r];
+            worst_msg = msg[r];
+        }
+    }
+    if (info_host) *info_host = total;
+    if (worst != NINT_OK) return fail(worst, -1, "%s", worst_msg.c_str());
+    if (total.n_panic)
+        return fail(NINT_E_PANIC, -1, "the reference implementation would panic on %llu point(s), first at index %llu",
+                    (unsigned long long)total.n_panic, (unsigned long long)total.first_panic);
+    if (total.n_error)
+        return fail(NINT_E_EXTRAPOLATE, -1,
+                    "attempted to interpolate at point beyond grid data: %llu point(s), first at index %llu",
+                    (unsigned long long)total.n_error, (unsigned long long)total.first_error);
     return NINT_OK;
 }
 
