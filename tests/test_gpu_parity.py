@@ -86,7 +86,8 @@ def _check(kind, lens, strategy, extrap, dtype, mode, n, seed, aos=False, frac_s
 
 
 FIXED_CASES = [(FIXED, (33,)), (FIXED, (17, 9)), (FIXED, (9, 7, 11))]
-ND_CASES = [(ND, (13,)), (ND, (7, 5)), (ND, (5, 4, 6)), (ND, (4, 3, 4, 3)), (ND, (3, 4, 3, 2, 3)), (ND, (2, 3, 2, 3, 2, 2))]
+ND_CASES = [(ND, (13,)), (ND, (7, 5)), (ND, (5, 4, 6)), (ND, (4, 3, 4, 3)), (ND, (3, 4, 3, 2, 3)), (ND, (2, 3, 2, 3, 2, 2)),
+            (ND, (2, 3, 2, 2, 3, 2, 2)), (ND, (2, 2, 3, 2, 2, 2, 3, 2))]
 
 
 def _combos(cases):
@@ -226,3 +227,32 @@ def test_division_fast_path_is_ieee_exact(dtype_code, name):
         assert lib.nint_selftest_divide(dtype_code, n, seed, C.byref(bad), C.byref(fast)) == 0
         assert bad.value == 0, f"{name}: {bad.value} of {n} quotients differ from IEEE division"
         assert fast.value > n // 4, f"{name}: fast path barely exercised ({fast.value})"
+
+
+def test_more_than_eight_dimensions_is_rejected():
+    import ninterp_b200 as nb
+
+    with pytest.raises(nb.EngineError):
+        nb.InterpND([[0., 1.]] * 9, np.zeros((2,) * 9))
+
+
+def test_plain_table_path_matches_packed(monkeypatch):
+    # NINT_PACK=0 keeps Linear on the plain C-order table (paired row loads) instead of the cell-packed copy
+    from gpu_util import assert_same, gpu_eval, make_pair
+
+    rng = np.random.default_rng(77)
+    for kind, lens, dtype in [(FIXED, (40,), np.float64), (FIXED, (21, 18), np.float32), (FIXED, (15, 16, 17), np.float64),
+                              (ND, (6, 5, 7, 4), np.float32)]:
+        axes = _axes(rng, lens, dtype, "uniform" if len(lens) == 3 else "nonuniform")
+        values = rng.uniform(-1, 1, lens).astype(dtype)
+        cols = _queries(rng, axes, 60000, dtype, 0.1)
+        for extrap in (ENABLE, CLAMP, WRAP):
+            monkeypatch.setenv("NINT_PACK", "0")
+            g0, o = make_pair(kind, axes, values, LIN, extrap, dtype=dtype)
+            monkeypatch.setenv("NINT_PACK", "1")
+            g1, _ = make_pair(kind, axes, values, LIN, extrap, dtype=dtype)
+            a, sa, _ = gpu_eval(g0, cols)
+            b, sb, _ = gpu_eval(g1, cols)
+            want, st_want = o.eval(cols, nthreads=O.max_threads())
+            assert_same(a, sa, want, st_want, f"plain {lens} {extrap}")
+            assert_same(b, sb, want, st_want, f"packed {lens} {extrap}")
