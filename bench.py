@@ -248,6 +248,29 @@ def time_steps(torch, dist, interp, cols, out, steps, warmup, world, sampler=Non
     return total_ms / 1e3, per_step, clocks
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's host threads (and so its pinned buffers, by first touch) to the CPUs NVML reports as local
+    to its GPU.  Host-side plumbing for the end-to-end leg; skipped silently when the topology is not visible."""
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid))
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64 + 1)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1}
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, allowed)
+            return sorted(allowed)
+    except Exception:
+        pass
+    return None
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -259,6 +282,7 @@ def run_b200(args, rank, local_rank, world):
         raise SystemExit("bench.py --impl b200 needs a CUDA device: ninterp_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = int(args.points)
@@ -383,6 +407,7 @@ def run_e2e(torch, dist, interp, cols, args, world, dev):
         dt = float(t.item())
     checksum = float(res_np[:: max(1, n // 1000)].sum())
     out = {"value": world * n * steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": n * 24 * world,
+           "host_cpus_rank0": len(os.sched_getaffinity(0)),
            "d2h_bytes_per_step": n * 8 * world, "points_per_step_per_gpu": n, "steps": steps, "ms_per_step": dt / steps * 1e3,
            "api": "nint_interpolate_batch_host (AoS points in pinned host memory -> host values)", "checksum": checksum}
     del pts, res
