@@ -16,9 +16,9 @@ cudaError_t launch_variant(const Params<T>& P, const LaunchCfg& cfg) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    // resident CTAs per SM for this kernel at this shared-memory size (cached; homogeneous GPUs)
-    static unsigned cached_smem = ~0u;
-    static int cached_bps = 0;
+    // resident CTAs per SM for this kernel at this shared-memory size (cached per host thread; homogeneous GPUs)
+    static thread_local unsigned cached_smem = ~0u;
+    static thread_local int cached_bps = 0;
     int bps = cached_bps;
     if (cached_smem != smem || bps == 0) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kBlock, smem);
