@@ -572,7 +572,9 @@ __device__ __forceinline__ bool verify_cell(const AxisRef<T>& a, T p, int k, T& 
 // collapse, an exact hit selects the node instead and is left to the general path.
 // kAxisFast guarantees every cell has a stored reciprocal (width inside the window) and the verified bracket
 // gives 0 <= a <= w, so only a tiny non-zero `a` can leave the window.
-template <class T, bool STRICT>
+// FIRST enables the p == g[0] clause; only the Clamp kernels use it (clamping produces that coordinate for
+// every point below the grid), elsewhere an exact lower-bound query is rare enough for the general path.
+template <class T, bool STRICT, bool FIRST>
 __device__ __forceinline__ bool verify_cell_linear(const AxisRef<T>& ax, T p, int k, T& a, T& w, T& R) {
     T G0, G1;
     ld_rec(ax.rec + 2 * k, G0, R);
@@ -580,12 +582,13 @@ __device__ __forceinline__ bool verify_cell_linear(const AxisRef<T>& ax, T p, in
     a = p - G0;
     w = G1 - G0;
     if (STRICT) return (G0 < p) && (p < G1) && in_div_window_pos(a);
+    if (!FIRST) return (G0 < p) && (p <= G1) && in_div_window_pos(a);
     const bool first = (k == 0) && (p == G0);
     return ((G0 < p && in_div_window_pos(a)) || first) && (p <= G1);
 }
 
 // The whole fast path for one point; false when anything about it needs the general path.
-template <class T, int N, bool IS_ND, int STRAT, bool UNI>
+template <class T, int N, bool IS_ND, int STRAT, bool UNI, bool FIRST>
 __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned char* pack, unsigned long long pol,
                                            const T (&p)[N], T& result) {
     constexpr bool kCollapse = IS_ND || (N == 1);
@@ -603,7 +606,7 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
 #pragma unroll
         for (int d = 0; d < N; ++d) {
             T a, w, r;
-            ok = verify_cell_linear<T, kCollapse>(load_axis<T>(P, pack, d), p[d], k[d], a, w, r) && ok;
+            ok = verify_cell_linear<T, kCollapse, FIRST>(load_axis<T>(P, pack, d), p[d], k[d], a, w, r) && ok;
             t[d] = div_markstein<T>(a, w, r);
         }
         T cube[1 << N];
@@ -726,7 +729,7 @@ __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_ke
         }
         unsigned status = NINT_STATUS_OK;
         T result;
-        const bool ok = fast_point<T, N, IS_ND, STRAT, UNI>(P, pack, pol, p, result);
+        const bool ok = fast_point<T, N, IS_ND, STRAT, UNI, PRE == kPreClamp>(P, pack, pol, p, result);
         if (!ok) {
             const Outcome<T> o = general_point<T, N, IS_ND, STRAT>(P, pack, q);
             result = o.value;
