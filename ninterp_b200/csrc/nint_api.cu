@@ -468,7 +468,7 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     nint::Params<T> P;
     fill_params<T>(h, P);
     for (int d = 0; d < h->ndim_eff; ++d) P.coords[d] = (const T*)cols[d];
-    P.coord_stride = coord_stride;
+    P.coord_stride = (unsigned)coord_stride;
     P.out = (T*)out;
     P.status = status;
     P.info = info_dev;
@@ -492,10 +492,20 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
 
 int launch(nint_handle* h, const void* const* cols, long long coord_stride, size_t n, void* out, uint8_t* status,
            nint_batch_info* info_dev, unsigned long long index_base, cudaStream_t stream) {
-    if (n == 0) return NINT_OK;
-    if (h->dtype == NINT_F64)
-        return launch_typed<double>(h, cols, coord_stride, n, out, status, info_dev, index_base, stream);
-    return launch_typed<float>(h, cols, coord_stride, n, out, status, info_dev, index_base, stream);
+    // the kernels index points with 32 bits: batches beyond kMaxLaunchPoints are split into back-to-back launches
+    const size_t es = elem_size(h->dtype);
+    for (size_t start = 0; start < n; start += nint::kMaxLaunchPoints) {
+        const size_t m = std::min<size_t>(nint::kMaxLaunchPoints, n - start);
+        const void* sub[NINT_MAX_NDIM] = {};
+        for (int d = 0; d < h->ndim_eff; ++d) sub[d] = (const unsigned char*)cols[d] + start * (size_t)coord_stride * es;
+        void* o = (unsigned char*)out + start * es;
+        uint8_t* st = status ? status + start : nullptr;
+        const int rc = (h->dtype == NINT_F64)
+                           ? launch_typed<double>(h, sub, coord_stride, m, o, st, info_dev, index_base + start, stream)
+                           : launch_typed<float>(h, sub, coord_stride, m, o, st, info_dev, index_base + start, stream);
+        if (rc != NINT_OK) return rc;
+    }
+    return NINT_OK;
 }
 
 int reset_info(nint_batch_info* info_dev, cudaStream_t stream) {

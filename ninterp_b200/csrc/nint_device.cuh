@@ -39,6 +39,8 @@ constexpr int kMaxDim = NINT_MAX_NDIM;
 #endif
 constexpr int kBlock = NINT_BLOCK;
 constexpr int kUnroll = NINT_UNROLL;
+// The point loop indexes with 32 bits (fewer registers, one-instruction address arithmetic).
+constexpr unsigned long long kMaxLaunchPoints = 1ull << 30;
 
 // per-axis flags (Params::flags)
 constexpr int kAxisUniform = 1;  // nodes are evenly spaced to within a small fraction of a cell
@@ -48,7 +50,7 @@ constexpr int kAxisFast = 2;     // axis may use the fast path: >= 2 nodes, stri
 template <class T>
 struct Params {
     const T* coords[kMaxDim];  // coordinate d of point i is coords[d][i * coord_stride]
-    long long coord_stride;    // 1 for columns (SoA), ndim for points (AoS)
+    unsigned coord_stride;     // 1 for columns (SoA), ndim for points (AoS)
     T* out;
     uint8_t* status;
     nint_batch_info* info;
@@ -56,8 +58,8 @@ struct Params {
     const T* cells;              // cell-packed copy of the table (2^N corners per cell, contiguous) or NULL
     const unsigned char* pack;   // axis pack in global memory
     unsigned pack_bytes;         // multiple of 16
-    unsigned long long n;
-    unsigned long long index_base;  // batch index of point 0 (host pipeline chunks)
+    unsigned long long n;           // points in this launch: at most kMaxLaunchPoints (the host splits larger batches)
+    unsigned long long index_base;  // batch index of point 0 (host pipeline chunks, split launches)
     T fill;
     int extrap;
     float l2_frac;  // fraction of the value table kept evict_last in L2 (0 = no hint)
@@ -610,7 +612,8 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
             t[d] = div_markstein<T>(a, w, r);
         }
         T cube[1 << N];
-        if (P.cells != nullptr) {
+        // the all-uniform kernels are only dispatched when the cell-packed table exists (nint_launch.cuh)
+        if (UNI || P.cells != nullptr) {
             long long cell = 0;
 #pragma unroll
             for (int d = 0; d < N; ++d) cell += (long long)k[d] * P.cstride[d];
@@ -693,21 +696,22 @@ __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_ke
     if (threadIdx.x < 4) s_info[threadIdx.x] = (threadIdx.x < 2) ? 0ull : ~0ull;
     __syncthreads();
 
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned n = (unsigned)P.n;  // <= 2^30, so i + stride cannot wrap
+    const unsigned stride = gridDim.x * blockDim.x;
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     Point<T, N> q;
-    if (i < P.n) {
+    if (i < n) {
 #pragma unroll
-        for (int d = 0; d < N; ++d) q.v[d] = ld_stream(P.coords[d] + i * P.coord_stride);
+        for (int d = 0; d < N; ++d) q.v[d] = ld_stream(P.coords[d] + (size_t)i * P.coord_stride);
     }
 #pragma unroll kUnroll
-    for (; i < P.n; i += stride) {
+    for (; i < n; i += stride) {
         // prefetch the next trip's coordinates
         Point<T, N> qn = q;
-        const unsigned long long in = i + stride;
-        if (in < P.n) {
+        const unsigned in = i + stride;
+        if (in < n) {
 #pragma unroll
-            for (int d = 0; d < N; ++d) qn.v[d] = ld_stream(P.coords[d] + in * P.coord_stride);
+            for (int d = 0; d < N; ++d) qn.v[d] = ld_stream(P.coords[d] + (size_t)in * P.coord_stride);
         }
 
         T p[N];
@@ -738,7 +742,7 @@ __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_ke
                 result = quiet_nan<T>();
                 const int slot = (status == NINT_STATUS_PANIC) ? 1 : 0;
                 atomicAdd(&s_info[slot], 1ull);
-                atomicMin(&s_info[2 + slot], i + P.index_base);
+                atomicMin(&s_info[2 + slot], (unsigned long long)i + P.index_base);
             }
         }
         st_stream(P.out + i, result);

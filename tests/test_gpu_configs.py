@@ -143,3 +143,37 @@ def test_large_batch_properties():
     node_cols = [ax_t[idx[k]].contiguous() for k in range(3)]
     vt = torch.from_numpy(v).to(dev)
     assert torch.equal(lin.interpolate_batch(node_cols), vt[idx[0], idx[1], idx[2]])
+
+
+def test_batch_larger_than_one_launch():
+    # the kernels index points with 32 bits and the host splits batches beyond 2^30 points into several launches:
+    # values, statuses and the batch-wide indices in nint_batch_info must be unaffected by the split
+    import ninterp_b200 as nb
+    import torch
+
+    dev = torch.device("cuda")
+    n = (1 << 30) + 12345
+    g = np.arange(64, dtype=np.float32)
+    v = (np.arange(64, dtype=np.float32) * 3.0).astype(np.float32)
+    interp = nb.Interp1D(g, v, nb.strategy.Linear, nb.Extrapolate.Error, dtype=np.float32)
+    x = torch.empty(n, dtype=torch.float32, device=dev)
+    x.uniform_(0.0, 63.0)
+    bad = [5, (1 << 30) - 1, (1 << 30) + 7, n - 1]
+    x[bad] = 100.0
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    status = torch.empty(n, dtype=torch.uint8, device=dev)
+    info = torch.zeros(4, dtype=torch.int64, device=dev)
+    interp.interpolate_batch([x], out=out, status=status, info=info)
+    torch.cuda.synchronize()
+    i = info.cpu().numpy().view(np.uint64)
+    assert int(i[0]) == 4 and int(i[1]) == 0 and int(i[2]) == 5
+    assert int(status.sum()) == 4 and status[bad].tolist() == [1, 1, 1, 1]
+    ok = status == 0
+    # f(x) = 3x on a uniform grid: exact up to rounding of the blend
+    assert float((out[ok] - 3.0 * x[ok]).abs().max()) < 1e-3
+    # second half (after the split) against the oracle on a sample
+    sl = slice((1 << 30) - 50000, (1 << 30) + 50000)
+    want, st = O.Oracle([g], v, LIN, ERROR, dtype=np.float32).eval([x[sl].cpu().numpy()])
+    from gpu_util import assert_same
+
+    assert_same(out[sl].cpu().numpy(), status[sl].cpu().numpy(), want, st, "split launch")
