@@ -583,10 +583,12 @@ __device__ __forceinline__ bool verify_cell_linear(const AxisRef<T>& ax, T p, in
     G1 = ax.g(k + 1);
     a = p - G0;
     w = G1 - G0;
-    if (STRICT) return (G0 < p) && (p < G1) && in_div_window_pos(a);
-    if (!FIRST) return (G0 < p) && (p <= G1) && in_div_window_pos(a);
+    // a = p - g[k] >= 2^-500 (tested on the high word) already implies g[k] < p; NaN and +inf pass that test
+    // but fail the upper bound
+    if (STRICT) return (p < G1) && in_div_window_pos(a);
+    if (!FIRST) return (p <= G1) && in_div_window_pos(a);
     const bool first = (k == 0) && (p == G0);
-    return ((G0 < p && in_div_window_pos(a)) || first) && (p <= G1);
+    return (in_div_window_pos(a) || first) && (p <= G1);
 }
 
 // The whole fast path for one point; false when anything about it needs the general path.
