@@ -616,10 +616,10 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
         T cube[1 << N];
         // the all-uniform kernels are only dispatched when the cell-packed table exists (nint_launch.cuh)
         if (UNI || P.cells != nullptr) {
-            long long cell = 0;
+            unsigned cell = 0;  // build_cells() only packs tables with fewer than 2^31 cells
 #pragma unroll
-            for (int d = 0; d < N; ++d) cell += (long long)k[d] * P.cstride[d];
-            ld_cells<(1 << N)>(P.cells + cell * (1 << N), cube);
+            for (int d = 0; d < N; ++d) cell += (unsigned)k[d] * (unsigned)P.cstride[d];
+            ld_cells<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
         } else {
             long long base = 0;
             long long step[N];
