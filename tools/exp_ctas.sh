@@ -5,9 +5,7 @@ for cfg in ${1:-"256:4 256:3"}; do
   IFS=: read b m x <<< "$cfg"
   export NINT_NVCC_EXTRA="-DNINT_BLOCK=$b -DNINT_MIN_CTAS=$m $x"
   python ninterp_b200/build.py > /dev/null 2>&1
-  for c in sorted random; do
-    echo "BLOCK=$b MIN_CTAS=$m $x case=$c: $(python tools/prof_case.py --case $c --points 4e8 --launches 4 | tail -1)"
-  done
+  echo "BLOCK=$b MIN_CTAS=$m $x sorted 1e9: $(python tools/prof_case.py --case sorted --points 1e9 --launches 4 | tail -1)"
 done
 export NINT_NVCC_EXTRA=""
 python ninterp_b200/build.py > /dev/null 2>&1
