@@ -34,11 +34,7 @@ constexpr int kMaxDim = NINT_MAX_NDIM;
 #ifndef NINT_BLOCK
 #define NINT_BLOCK 256
 #endif
-#ifndef NINT_UNROLL
-#define NINT_UNROLL 1  // trips of the point loop unrolled together (tuning knob; measured: see tools/exp_ctas.sh)
-#endif
 constexpr int kBlock = NINT_BLOCK;
-constexpr int kUnroll = NINT_UNROLL;
 // The point loop indexes with 32 bits (fewer registers, one-instruction address arithmetic).
 constexpr unsigned long long kMaxLaunchPoints = 1ull << 30;
 
@@ -142,36 +138,8 @@ __device__ __forceinline__ void ld_table2(const float* p, unsigned long long pol
     asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(a), "=f"(b) : "l"(p), "l"(pol));
 }
 
-// One cell of the cell-packed table: COUNT = 2^N contiguous elements, loaded 32 bytes at a time
-// (LDG.256 on sm_100) or with the widest load the block size allows.
-template <int COUNT>
-__device__ __forceinline__ void ld_block(const double* p, unsigned long long pol, double (&v)[COUNT]) {
-    if constexpr (COUNT >= 4) {
-#pragma unroll
-        for (int k = 0; k < COUNT; k += 4)
-            asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
-                         : "=d"(v[k]), "=d"(v[k + 1]), "=d"(v[k + 2]), "=d"(v[k + 3]) : "l"(p + k), "l"(pol));
-    } else {
-        ld_table2(p, pol, v[0], v[1]);
-    }
-}
-template <int COUNT>
-__device__ __forceinline__ void ld_block(const float* p, unsigned long long pol, float (&v)[COUNT]) {
-    if constexpr (COUNT >= 8) {
-#pragma unroll
-        for (int k = 0; k < COUNT; k += 8)
-            asm volatile("ld.global.nc.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-                         : "=f"(v[k]), "=f"(v[k + 1]), "=f"(v[k + 2]), "=f"(v[k + 3]), "=f"(v[k + 4]), "=f"(v[k + 5]),
-                           "=f"(v[k + 6]), "=f"(v[k + 7]) : "l"(p + k), "l"(pol));
-    } else if constexpr (COUNT == 4) {
-        asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p), "l"(pol));
-    } else {
-        ld_table2(p, pol, v[0], v[1]);
-    }
-}
-
-// Same, without a cache policy operand (plain LRU): used for the cell-packed table.
+// One cell of the cell-packed table: COUNT = 2^N contiguous elements, loaded 32 bytes at a time (LDG.256 on
+// sm_100) or with the widest load the block size allows; plain LRU, no cache-policy operand.
 template <int COUNT>
 __device__ __forceinline__ void ld_cells(const double* p, double (&v)[COUNT]) {
     if constexpr (COUNT >= 4) {
@@ -706,7 +674,6 @@ __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_ke
 #pragma unroll
         for (int d = 0; d < N; ++d) q.v[d] = ld_stream(P.coords[d] + (size_t)i * P.coord_stride);
     }
-#pragma unroll kUnroll
     for (; i < n; i += stride) {
         // prefetch the next trip's coordinates
         Point<T, N> qn = q;
