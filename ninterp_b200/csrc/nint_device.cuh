@@ -9,9 +9,9 @@
 // -use_fast_math.  The only FMAs are explicit ones inside div_markstein(), which reproduce IEEE division.
 //
 // Structure of a point's evaluation
-//   fast path   guess the cell on every axis, VERIFY it against the node values (g[k] < p <= g[k+1]),
-//               gather the cell, blend.  A verified cell implies the point is in range and finite, so
-//               the fast path is the same for every Extrapolate policy.
+//   fast path   guess the cell on every axis, VERIFY it against the node values (g[k] < p <= g[k+1]) while
+//               computing the weights, gather the cell, blend.  A verified cell implies the point is in
+//               range and finite, so the fast path is the same for every Extrapolate policy.
 //   general     everything else (out of range, NaN/inf, exact node hits, degenerate axes, duplicate
 //               nodes, wide buckets): an out-of-line restatement of the reference's control flow.
 //
@@ -525,7 +525,7 @@ __device__ __forceinline__ bool guess_cell(const AxisRef<T>& a, T p, int& k) {
     return ok;
 }
 
-// Fast path, phase 3: g[k] < p <= g[k+1] (strictly below g[k+1] where an exact node hit must collapse the
+// Fast path, phase 2: g[k] < p <= g[k+1] (strictly below g[k+1] where an exact node hit must collapse the
 // axis).  A verified cell is the cell the reference picks: find_nearest_index returns the cell to the left
 // of an exact hit and maps `== last` to L-2, both of which satisfy the same inequality when the nodes are
 // strictly increasing; and it implies that p is in range and not NaN.
