@@ -222,10 +222,15 @@ def fill_cell_sorted(torch, cols, dev, seed, chunk=1 << 26, GRID=GRID):
 
 
 def time_steps(torch, dist, interp, cols, out, steps, warmup, world, sampler=None):
-    """W warm-up + K timed steps; returns (max-over-ranks seconds for K steps, per-step kernel ms list)."""
+    """W warm-up + K timed steps; returns (max-over-ranks seconds for K steps, per-step kernel ms list, clocks).
+    time_steps.launches = kernels this rank launched inside the timed region (a batch call is one launch, or an
+    order probe plus its passes on tables well beyond L2)."""
+    from ninterp_b200 import _lib
+
     for _ in range(warmup):
         interp.interpolate_batch(cols, out=out)
     torch.cuda.synchronize()
+    launches0 = _lib.lib().nint_launch_count()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -237,6 +242,7 @@ def time_steps(torch, dist, interp, cols, out, steps, warmup, world, sampler=Non
         interp.interpolate_batch(cols, out=out)
         ev[k + 1].record()
     torch.cuda.synchronize()
+    time_steps.launches = _lib.lib().nint_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
     total_ms = ev[0].elapsed_time(ev[steps])
@@ -293,10 +299,11 @@ def run_b200(args, rank, local_rank, world):
     cols = gen_random(torch, n, dev, seed=1234567890 + rank)
     out = torch.empty(n, dtype=torch.float64, device=dev)
 
-    launches0 = lib.nint_launch_count()
     sampler = ClockSampler(local_rank)
     secs, per_step, clocks = time_steps(torch, dist, interp, cols, out, args.steps, args.warmup, world, sampler)
-    launches = torch.tensor([lib.nint_launch_count() - launches0 - args.warmup], dtype=torch.int64, device=dev)
+    launches_rank = int(time_steps.launches)
+    launches = torch.tensor([launches_rank], dtype=torch.int64, device=dev)
+    order = int(lib.nint_last_query_order(interp._h))  # 0 no probe, 1 coherent, 2 incoherent (slab passes)
     if world > 1:
         dist.all_reduce(launches)
     value = world * n * args.steps / secs / 1e9
@@ -309,15 +316,22 @@ def run_b200(args, rank, local_rank, world):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = n * BYTES_PER_POINT / (kernel_ms * 1e-3) / 1e9
+    # One batch call is the unit of accounting: a single interp_kernel launch, or (incoherent queries on a table
+    # well beyond L2) the order probe plus the slab passes, whose summed time and summed DRAM traffic are reported.
+    per_call = launches_rank // max(args.steps, 1)
+    slab = order == 2
     traffic = None
     try:
-        traffic = json.load(open(ROOT / "profiles" / "traffic.json")).get("interp3d_linear_f64_uniform_random_bytes_per_launch")
+        key = "interp3d_linear_f64_uniform_random_slab_bytes_per_call" if slab else "interp3d_linear_f64_uniform_random_bytes_per_launch"
+        traffic = json.load(open(ROOT / "profiles" / "traffic.json")).get(key)
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "kernel": "interp_kernel<double,3,fixed,Linear,smem,plain,uniform>", "kernel_ms": kernel_ms,
-                "algorithmic_bytes_per_point": BYTES_PER_POINT, "points_per_launch": n}
+                "kernel": (f"{per_call - 2} x slab_kernel<double,3,fixed,plain,uniform> + order_probe_kernel per batch call"
+                           if slab else "interp_kernel<double,3,fixed,Linear,smem,plain,uniform>"),
+                "kernel_ms": kernel_ms, "launches_per_call": per_call,
+                "algorithmic_bytes_per_point": BYTES_PER_POINT, "points_per_call": n}
 
     # parity sample of the main workload, kept for the cpu_baseline leg
     sample_n = 0

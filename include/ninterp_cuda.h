@@ -167,6 +167,11 @@ NINT_API int nint_interpolate_batch_host_multi(nint_handle* const* handles, int 
  * (three/mod.rs:193-238): point_len != ndim gives NINT_E_POINT_LENGTH. */
 NINT_API int nint_interpolate(nint_handle* h, const void* point, size_t point_len, void* out);
 
+/* Diagnostics: how the most recent batch on this handle was classified by the on-device order probe that runs
+ * for Linear on tables well beyond L2: 0 = no probe ran, 1 = coherent (single pass on the
+ * cell-packed table), 2 = incoherent (slab passes on the plain table).  Synchronises the device. */
+NINT_API int nint_last_query_order(nint_handle* h);
+
 /* Pinned host memory for nint_interpolate_batch_host. */
 NINT_API int nint_host_alloc(void** ptr, size_t bytes);
 NINT_API int nint_host_free(void* ptr);

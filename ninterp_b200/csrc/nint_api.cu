@@ -125,6 +125,9 @@ struct nint_handle {
     int sm_count = 0;
     // scratch for the synchronous entry points
     nint_batch_info* d_info = nullptr;
+    int* d_mode = nullptr;  // ring of query-order flags written by the order probe (one per batch call)
+    std::atomic<unsigned> mode_slot{0};
+    int* last_mode = nullptr;  // flag of the most recent probed batch (diagnostics)
     void* d_pt = nullptr;   // one point
     void* d_res = nullptr;  // one value + status byte
     Pipeline pipe;
@@ -457,6 +460,35 @@ void fill_params(const nint_handle* h, nint::Params<T>& P) {
     }
 }
 
+// Number of slab passes for a batch of n points; 0 = no order probe, the batch runs as a single pass on the
+// cell-packed table.  Slab passes serve incoherent queries when the packed table is well beyond L2: each pass
+// gathers from a slab of the plain table that stays L2-resident under the query streams.
+// They need Linear, axes staged in shared memory, a fast-path axis 0 with enough cells, and a policy that does
+// not re-map coordinates across axes (not Wrap).  More than kSlabMaxPasses passes cost more than they save.
+// NINT_SLABS=0 disables the mode, NINT_SLABS=k forces k passes; NINT_SLAB_MIN_BYTES / NINT_SLAB_MIN_POINTS
+// override the thresholds (tests).
+constexpr double kSlabBytes = 48.0 * 1024 * 1024;  // slab size that L2 keeps resident beside the streams
+constexpr int kSlabMaxPasses = 6;
+int slab_windows(const nint_handle* h, size_t n) {
+    const char* e_bytes = std::getenv("NINT_SLAB_MIN_BYTES");
+    const char* e_points = std::getenv("NINT_SLAB_MIN_POINTS");
+    const char* e_on = std::getenv("NINT_SLABS");
+    const long long min_bytes = e_bytes ? std::atoll(e_bytes) : 256ll << 20;
+    const long long min_points = e_points ? std::atoll(e_points) : 1ll << 22;
+    const int forced = e_on ? std::atoi(e_on) : -1;
+    if (forced == 0 || h->constant || h->strategy != NINT_LINEAR || h->extrap == NINT_EXTRAPOLATE_WRAP || !h->smem_axes) return 0;
+    if (!(h->ax[0].flags & nint::kAxisFast) || (long long)n < min_points) return 0;
+    const int cells0 = (int)h->axis_len[0] - 1;
+    if (forced > 0) return (cells0 >= 4 * forced) ? forced : 0;
+    // what the single pass would gather from: the packed table when there is one
+    const double plain = (double)h->values_len * (double)elem_size(h->dtype);
+    const double single = h->d_cells ? plain * (double)(1u << h->ndim_eff) : plain;
+    if (single < (double)min_bytes) return 0;
+    const int w = std::max(1, (int)std::ceil(plain / kSlabBytes));
+    if (w > kSlabMaxPasses || cells0 < 4 * w) return 0;
+    return w;
+}
+
 template <class T>
 int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride, size_t n, void* out,
                  uint8_t* status, nint_batch_info* info_dev, unsigned long long index_base, cudaStream_t stream) {
@@ -485,8 +517,37 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     cfg.smem_bytes = h->pack_bytes;
     cfg.sm_count = h->sm_count;
     cfg.stream = stream;
-    cudaError_t e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : nint::launch_fixed<T>(P, cfg);
+    cfg.slab = 0;
+    const int windows = slab_windows(h, n);
+    if (windows <= 0) {
+        cudaError_t e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : nint::launch_fixed<T>(P, cfg);
+        if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+        return NINT_OK;
+    }
+    // Large table, Linear: let the device decide from a sample of the batch whether the queries are coherent
+    // (single pass on the cell-packed table) or not (slab passes on the plain table); enqueue both.
+    int* flag = h->d_mode + (h->mode_slot.fetch_add(1) & 63u);
+    h->last_mode = flag;
+    cudaError_t e = nint::launch_order_probe<T>(P, flag, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "order probe launch");
+    P.mode_flag = flag;
+    P.mode_want = nint::kModeCoherent;
+    e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : nint::launch_fixed<T>(P, cfg);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    P.mode_want = nint::kModeRandom;
+    cfg.slab = 1;
+    const int cells0 = (int)h->axis_len[0] - 1;
+    const int per = (cells0 + windows - 1) / windows;
+    for (int w = 0; w < windows; ++w) {
+        // window w holds the points whose axis-0 cell is in [w * per, (w + 1) * per): node values as thresholds
+        const T* g0 = (const T*)h->axes_host[0].data();
+        P.win_lo_x = g0[std::min(cells0, w * per)];
+        P.win_hi_x = g0[std::min(cells0, (w + 1) * per)];
+        P.win_first = (w == 0);
+        P.win_last = (w == windows - 1);
+        e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : nint::launch_fixed<T>(P, cfg);
+        if (e != cudaSuccess) return cuda_fail(e, "slab kernel launch");
+    }
     return NINT_OK;
 }
 
@@ -662,6 +723,7 @@ int nint_create(int device, int kind, int dtype, int ngrid, const size_t* axis_l
     if (rc == NINT_OK) {
         cudaError_t e2 = cudaMalloc((void**)&h->d_info, sizeof(nint_batch_info));
         if (e2 == cudaSuccess) e2 = cudaMalloc(&h->d_pt, NINT_MAX_NDIM * sizeof(double));
+        if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&h->d_mode, 64 * sizeof(int));
         if (e2 == cudaSuccess) e2 = cudaMalloc(&h->d_res, 16);
         if (e2 != cudaSuccess) rc = cuda_fail(e2, "cudaMalloc");
     }
@@ -682,6 +744,7 @@ void nint_destroy(nint_handle* h) {
         if (h->d_cells) cudaFree(h->d_cells);
         if (h->d_pack) cudaFree(h->d_pack);
         if (h->d_info) cudaFree(h->d_info);
+        if (h->d_mode) cudaFree(h->d_mode);
         if (h->d_pt) cudaFree(h->d_pt);
         if (h->d_res) cudaFree(h->d_res);
     }
@@ -935,6 +998,16 @@ int nint_host_alloc(void** ptr, size_t bytes) {
 int nint_host_free(void* ptr) {
     NINT_CUDA(cudaFreeHost(ptr));
     return NINT_OK;
+}
+
+int nint_last_query_order(nint_handle* h) {
+    if (!h) return fail(NINT_E_INVALID_ARGUMENT, -1, "handle is NULL");
+    if (!h->last_mode) return 0;
+    DeviceGuard guard(h->device);
+    int v = 0;
+    NINT_CUDA(cudaDeviceSynchronize());
+    NINT_CUDA(cudaMemcpy(&v, h->last_mode, sizeof v, cudaMemcpyDeviceToHost));
+    return v;
 }
 
 const char* nint_last_error_message(void) { return t_err_msg.c_str(); }

@@ -40,6 +40,9 @@ constexpr unsigned long long kMaxLaunchPoints = 1ull << 30;
 
 // per-axis flags (Params::flags)
 constexpr int kAxisUniform = 1;  // nodes are evenly spaced to within a small fraction of a cell
+constexpr int kModeCoherent = 1;  // consecutive queries mostly fall into neighbouring cells
+constexpr int kModeRandom = 2;    // they do not: evaluate in slab passes
+
 constexpr int kAxisFast = 2;     // axis may use the fast path: >= 2 nodes, strictly increasing, every cell
                                  // width inside the division window (all reciprocals stored)
 
@@ -59,6 +62,13 @@ struct Params {
     T fill;
     int extrap;
     float l2_frac;  // fraction of the value table kept evict_last in L2 (0 = no hint)
+    // Query-order modes (see "slab passes" below).  mode_flag is written by order_probe_kernel; a launch runs
+    // only if *mode_flag == mode_want (NULL: always).  A slab launch evaluates the points whose axis-0 coordinate
+    // lies in (win_lo_x, win_hi_x]; the first window is open below (and takes NaN), the last is open above.
+    const int* mode_flag;
+    int mode_want;
+    T win_lo_x, win_hi_x;
+    int win_first, win_last;
     int L[kMaxDim];
     int M[kMaxDim];
     int flags[kMaxDim];
@@ -560,7 +570,7 @@ __device__ __forceinline__ bool verify_cell_linear(const AxisRef<T>& ax, T p, in
 }
 
 // The whole fast path for one point; false when anything about it needs the general path.
-template <class T, int N, bool IS_ND, int STRAT, bool UNI, bool FIRST>
+template <class T, int N, bool IS_ND, int STRAT, bool UNI, bool FIRST, bool PLAIN = false>
 __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned char* pack, unsigned long long pol,
                                            const T (&p)[N], T& result) {
     constexpr bool kCollapse = IS_ND || (N == 1);
@@ -583,7 +593,7 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
         }
         T cube[1 << N];
         // the all-uniform kernels are only dispatched when the cell-packed table exists (nint_launch.cuh)
-        if (UNI || P.cells != nullptr) {
+        if (!PLAIN && (UNI || P.cells != nullptr)) {
             unsigned cell = 0;  // build_cells() only packs tables with fewer than 2^31 cells
 #pragma unroll
             for (int d = 0; d < N; ++d) cell += (unsigned)k[d] * (unsigned)P.cstride[d];
@@ -650,6 +660,7 @@ constexpr int min_ctas(int n, int elem_bytes) {
 template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE, bool UNI>
 __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_kernel(const __grid_constant__ Params<T> P) {
     extern __shared__ __align__(16) unsigned char smem_pack[];
+    if (P.mode_flag != nullptr && *P.mode_flag != P.mode_want) return;  // the other query-order mode runs this batch
     const unsigned char* pack;
     if (SMEM) {
         const uint4* src = reinterpret_cast<const uint4*>(P.pack);
@@ -734,6 +745,170 @@ __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_ke
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Slab passes for incoherent queries on tables larger than L2 (Linear).
+//
+// When consecutive queries land in unrelated cells and the table does not fit L2, every corner load is a DRAM
+// (and, for the packed table, a TLB) miss.  The batch is then evaluated in W launches; launch w only evaluates
+// the points whose axis-0 cell lies in slab w of the plain table, so the part of the table being gathered fits
+// L2.  Warps work on their own: a warp scans a span of kSlabSpan points (axis-0 coordinate only), appends the
+// members to its list in shared memory (ballot + popc, no atomics) and evaluates them 32 at a time, so every
+// lane is busy whatever the membership pattern; what is left over (< 32) waits in a register for the next span.
+// Which mode a batch uses is decided on the device by order_probe_kernel from a sample of the batch; both kinds
+// of launch are always enqueued and the ones of the other mode return at once.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSlabPer = 8;                   // points per lane and span
+constexpr unsigned kSlabSpan = 32u * kSlabPer;  // points a warp scans at a time
+
+
+template <class T, int N, bool IS_ND, int PRE, bool UNI>
+__global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) slab_kernel(const __grid_constant__ Params<T> P) {
+    extern __shared__ __align__(16) unsigned char smem_pack[];
+    __shared__ unsigned short s_list[kBlock / 32][kSlabSpan];
+    __shared__ unsigned long long s_info[4];  // n_error, n_panic, first_error, first_panic
+    if (P.mode_flag != nullptr && *P.mode_flag != P.mode_want) return;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(P.pack);
+        uint4* dst = reinterpret_cast<uint4*>(smem_pack);
+        for (unsigned i = threadIdx.x; i < P.pack_bytes / 16u; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    const unsigned char* pack = smem_pack;
+    const unsigned long long pol = make_table_policy(1.0f);  // the slab stays, the query streams go first
+    if (threadIdx.x < 4) s_info[threadIdx.x] = (threadIdx.x < 2) ? 0ull : ~0ull;
+    __syncthreads();
+    const unsigned n = (unsigned)P.n;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned short* list = s_list[threadIdx.x >> 5];
+    const unsigned nspans = (n + kSlabSpan - 1) / kSlabSpan;
+    const unsigned warps = gridDim.x * (kBlock / 32);
+    // members that did not fill a group of 32 wait here, one per lane in lanes [0, ncarry)
+    unsigned carry = 0, ncarry = 0;
+
+    auto fetch = [&](unsigned i, Point<T, N>& q) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) q.v[d] = ld_stream(P.coords[d] + (size_t)i * P.coord_stride);
+    };
+    auto evaluate = [&](unsigned i, const Point<T, N>& q) {
+        T p[N];
+#pragma unroll
+        for (int d = 0; d < N; ++d) p[d] = (PRE == kPreClamp) ? clamp_coord(q.v[d], P.g0[d], P.gl[d]) : q.v[d];
+        unsigned status = NINT_STATUS_OK;
+        T result;
+        const bool ok = fast_point<T, N, IS_ND, NINT_LINEAR, UNI, PRE == kPreClamp, true>(P, pack, pol, p, result);
+        if (!ok) {
+            const Outcome<T> o = general_point<T, N, IS_ND, NINT_LINEAR>(P, pack, q);
+            result = o.value;
+            status = o.status;
+            if (status != NINT_STATUS_OK) {
+                result = quiet_nan<T>();
+                const int slot = (status == NINT_STATUS_PANIC) ? 1 : 0;
+                atomicAdd(&s_info[slot], 1ull);
+                atomicMin(&s_info[2 + slot], (unsigned long long)i + P.index_base);
+            }
+        }
+        st_stream(P.out + i, result);
+        if (P.status) P.status[i] = (uint8_t)status;
+    };
+
+    for (unsigned span = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); span < nspans; span += warps) {
+        const unsigned base = span * kSlabSpan;
+        // axis-0 coordinates of the span, all requested before the first is used
+        T xs[kSlabPer];
+#pragma unroll
+        for (int r = 0; r < kSlabPer; ++r) {
+            const unsigned j = base + r * 32u + lane;
+            xs[r] = (j < n) ? ld_stream(P.coords[0] + (size_t)j * P.coord_stride) : quiet_nan<T>();
+        }
+        // members: axis-0 coordinate in (win_lo_x, win_hi_x]; the first window also takes everything below and
+        // NaN, the last everything above.  Listed as offsets into the span, in any order.
+        unsigned count = 0;
+#pragma unroll
+        for (int r = 0; r < kSlabPer; ++r) {
+            const unsigned j = base + r * 32u + lane;
+            const T x = xs[r];
+            const bool above = P.win_first ? true : (x > P.win_lo_x);
+            const bool below = P.win_last ? true : !(x > P.win_hi_x);
+            const bool mine = (j < n) && above && below;
+            const unsigned bal = __ballot_sync(0xffffffffu, mine);
+            if (mine) list[count + __popc(bal & lt)] = (unsigned short)(r * 32u + lane);
+            count += __popc(bal);
+        }
+        __syncwarp();
+        // groups of 32: the waiting members first, the rest from the list; the coordinates of the next group
+        // are in flight while the current one is evaluated
+        unsigned pos = 0;
+        if (ncarry + count >= 32u) {
+            unsigned i = (lane < ncarry) ? carry : base + list[lane - ncarry];
+            Point<T, N> q;
+            fetch(i, q);
+            pos = 32u - ncarry;
+            ncarry = 0;
+            while (count - pos >= 32u) {
+                const unsigned in = base + list[pos + lane];
+                Point<T, N> qn;
+                fetch(in, qn);
+                evaluate(i, q);
+                i = in;
+                q = qn;
+                pos += 32u;
+            }
+            evaluate(i, q);
+        }
+        const unsigned rem = count - pos;
+        if (lane >= ncarry && lane < ncarry + rem) carry = base + list[pos + lane - ncarry];
+        ncarry += rem;
+        __syncwarp();
+    }
+    if (lane < ncarry) {
+        Point<T, N> q;
+        fetch(carry, q);
+        evaluate(carry, q);
+    }
+    if (P.info) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (s_info[0]) {
+                atomicAdd((unsigned long long*)&P.info->n_error, s_info[0]);
+                atomicMin((unsigned long long*)&P.info->first_error, s_info[2]);
+            }
+            if (s_info[1]) {
+                atomicAdd((unsigned long long*)&P.info->n_panic, s_info[1]);
+                atomicMin((unsigned long long*)&P.info->first_panic, s_info[3]);
+            }
+        }
+    }
+}
+
+// Decides the query-order mode of a batch from 4096 pairs of consecutive points spread over it: coherent when at
+// least half of the pairs sit in the same or a neighbouring axis-0 cell.  One CTA; axes are read from global memory.
+template <class T>
+__global__ void __launch_bounds__(256) order_probe_kernel(const __grid_constant__ Params<T> P, int* __restrict__ mode_flag) {
+    __shared__ int s_near, s_valid;
+    if (threadIdx.x == 0) s_near = s_valid = 0;
+    __syncthreads();
+    const AxisRef<T> a0 = load_axis<T>(P, P.pack, 0);
+    const unsigned n = (unsigned)P.n;
+    int near = 0, valid = 0;
+    for (unsigned s = threadIdx.x; s < 4096u; s += blockDim.x) {
+        const unsigned i = (unsigned)(((unsigned long long)s * (unsigned long long)(n - 1u)) >> 12);
+        if (i + 1u >= n) continue;
+        const T x0 = __ldg(P.coords[0] + (size_t)i * P.coord_stride);
+        const T x1 = __ldg(P.coords[0] + (size_t)(i + 1u) * P.coord_stride);
+        int k0, k1;
+        const bool ok0 = guess_cell<T, false>(a0, x0, k0);
+        const bool ok1 = guess_cell<T, false>(a0, x1, k1);
+        if (ok0 && ok1) {
+            ++valid;
+            if (abs(k0 - k1) <= 1) ++near;
+        }
+    }
+    atomicAdd(&s_near, near);
+    atomicAdd(&s_valid, valid);
+    __syncthreads();
+    if (threadIdx.x == 0) *mode_flag = (2 * s_near >= s_valid) ? kModeCoherent : kModeRandom;
+}
+
 // 0-D InterpND (n/mod.rs:104-110): every point evaluates to the single stored value.
 template <class T>
 __global__ void __launch_bounds__(kBlock) constant_kernel(const T* __restrict__ values, T* __restrict__ out,
@@ -773,6 +948,7 @@ struct LaunchCfg {
     int strategy;
     int smem_axes;  // stage the axis pack in shared memory
     int all_uniform;  // every axis is uniform and fast-path eligible
+    int slab;         // launch slab_kernel (Params::win_*) instead of interp_kernel
     unsigned smem_bytes;
     int sm_count;
     void* stream;
@@ -782,6 +958,8 @@ template <class T>
 cudaError_t launch_fixed(const Params<T>& P, const LaunchCfg& cfg);
 template <class T>
 cudaError_t launch_nd(const Params<T>& P, const LaunchCfg& cfg);
+template <class T>
+cudaError_t launch_order_probe(const Params<T>& P, int* mode_flag, void* stream);
 template <class T>
 cudaError_t launch_pack_cells(const Params<T>& P, int ndim, T* out, unsigned long long total, int sm_count, void* stream);
 template <class T>

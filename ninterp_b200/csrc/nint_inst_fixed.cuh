@@ -25,6 +25,14 @@ cudaError_t dispatch_strategy(const Params<T>& P, const LaunchCfg& cfg) {
 
 template <>
 cudaError_t launch_fixed<NINT_T>(const Params<NINT_T>& P, const LaunchCfg& cfg) {
+    if (cfg.slab) {
+        switch (cfg.ndim) {
+        case 1: return launch_slab<NINT_T, 1, false>(P, cfg);
+        case 2: return launch_slab<NINT_T, 2, false>(P, cfg);
+        case 3: return launch_slab<NINT_T, 3, false>(P, cfg);
+        default: return cudaErrorInvalidValue;
+        }
+    }
     switch (cfg.ndim) {
     case 1:
         if (cfg.strategy == NINT_LEFT_NEAREST) return dispatch_smem<NINT_T, 1, NINT_LEFT_NEAREST>(P, cfg);
@@ -34,6 +42,13 @@ cudaError_t launch_fixed<NINT_T>(const Params<NINT_T>& P, const LaunchCfg& cfg) 
     case 3: return dispatch_strategy<NINT_T, 3>(P, cfg);
     default: return cudaErrorInvalidValue;
     }
+}
+
+template <>
+cudaError_t launch_order_probe<NINT_T>(const Params<NINT_T>& P, int* mode_flag, void* stream) {
+    order_probe_kernel<NINT_T><<<1, 256, 0, (cudaStream_t)stream>>>(P, mode_flag);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
 }
 
 template <>

@@ -22,6 +22,19 @@ cudaError_t dispatch_nd(const Params<T>& P, const LaunchCfg& cfg) {
 
 template <>
 cudaError_t launch_nd<NINT_T>(const Params<NINT_T>& P, const LaunchCfg& cfg) {
+    if (cfg.slab) {
+        switch (cfg.ndim) {
+        case 1: return launch_slab<NINT_T, 1, true>(P, cfg);
+        case 2: return launch_slab<NINT_T, 2, true>(P, cfg);
+        case 3: return launch_slab<NINT_T, 3, true>(P, cfg);
+        case 4: return launch_slab<NINT_T, 4, true>(P, cfg);
+        case 5: return launch_slab<NINT_T, 5, true>(P, cfg);
+        case 6: return launch_slab<NINT_T, 6, true>(P, cfg);
+        case 7: return launch_slab<NINT_T, 7, true>(P, cfg);
+        case 8: return launch_slab<NINT_T, 8, true>(P, cfg);
+        default: return cudaErrorInvalidValue;
+        }
+    }
     switch (cfg.ndim) {
     case 1: return dispatch_nd<NINT_T, 1>(P, cfg);
     case 2: return dispatch_nd<NINT_T, 2>(P, cfg);

@@ -256,3 +256,54 @@ def test_plain_table_path_matches_packed(monkeypatch):
             want, st_want = o.eval(cols, nthreads=O.max_threads())
             assert_same(a, sa, want, st_want, f"plain {lens} {extrap}")
             assert_same(b, sb, want, st_want, f"packed {lens} {extrap}")
+
+
+def test_slab_passes_and_order_probe(monkeypatch):
+    # Linear on tables beyond L2 lets an on-device probe choose between one pass on the cell-packed table
+    # (coherent queries) and slab passes on the plain table (incoherent ones).  Force the mode on small tables.
+    from gpu_util import assert_same, expected_info, gpu_eval, make_pair
+
+    from ninterp_b200 import _lib
+
+    monkeypatch.setenv("NINT_SLAB_MIN_BYTES", "0")
+    monkeypatch.setenv("NINT_SLAB_MIN_POINTS", "0")
+    rng = np.random.default_rng(99)
+    n = 300_001
+    for kind, lens, dtype, mode, passes in [(FIXED, (40, 9, 7), np.float64, "uniform", 3), (FIXED, (33, 12), np.float32, "nonuniform", 2),
+                                            (FIXED, (64,), np.float64, "nonuniform", 5), (ND, (17, 5, 4, 3), np.float32, "nonuniform", 4),
+                                            (ND, (20, 6, 5), np.float64, "uniform", 1)]:
+        monkeypatch.setenv("NINT_SLABS", str(passes))
+        axes = _axes(rng, lens, dtype, mode)
+        values = rng.uniform(-1, 1, lens).astype(dtype)
+        for extrap in (ERROR, CLAMP, ENABLE, FILL):
+            g, o = make_pair(kind, axes, values, LIN, extrap, fill=-2.5, dtype=dtype)
+            cols = _queries(rng, axes, n, dtype, 0.05)
+            # every axis-0 node (the pass boundaries are nodes), their neighbours, and the non-finite values
+            a0 = np.asarray(axes[0], dtype=dtype)
+            special = np.concatenate([a0, np.nextafter(a0, dtype(np.inf)), np.nextafter(a0, dtype(-np.inf)),
+                                      np.array([np.nan, np.inf, -np.inf], dtype=dtype)])
+            where = rng.choice(n, special.size, replace=False)
+            cols[0][where] = special
+            # incoherent order
+            got, st, info = gpu_eval(g, cols)
+            want, st_want = o.eval(cols, nthreads=O.max_threads())
+            assert_same(got, st, want, st_want, f"slab random {lens} {extrap}")
+            assert info == expected_info(st_want)
+            assert _lib.lib().nint_last_query_order(g._h) == 2
+            # coherent order: sorted along axis 0
+            order = np.argsort(cols[0], kind="stable")
+            cols_s = [c[order] for c in cols]
+            got, st, info = gpu_eval(g, cols_s)
+            assert_same(got, st, want[order], st_want[order], f"slab sorted {lens} {extrap}")
+            assert info == expected_info(st_want[order])
+            assert _lib.lib().nint_last_query_order(g._h) == 1
+            # array-of-points input takes the same route
+            got, st, _ = gpu_eval(g, cols, aos=True)
+            assert_same(got, st, want, st_want, f"slab aos {lens} {extrap}")
+    # Wrap re-maps every axis when one is out of range, so it stays on the single-pass kernels
+    monkeypatch.setenv("NINT_SLABS", "2")
+    g, o = make_pair(FIXED, _axes(rng, (30, 8), np.float64), rng.uniform(-1, 1, (30, 8)), LIN, WRAP)
+    cols = _queries(rng, g.data.grid, 50_000, np.float64, 0.05)
+    got, st, _ = gpu_eval(g, cols)
+    assert_same(got, st, *o.eval(cols), "wrap stays single pass")
+    assert _lib.lib().nint_last_query_order(g._h) == 0
