@@ -208,8 +208,11 @@ void build_lut(int dtype, const void* nodes, int L, int M, double g0, double inv
     }
 }
 
-constexpr unsigned kSmemPreferred = 64u * 1024u;   // keeps several CTAs resident per SM
-constexpr unsigned kSmemLimit = 200u * 1024u;      // below the 227 KB opt-in ceiling
+// Axis packs up to this size are staged in shared memory by every CTA; larger ones are read through L1 from
+// global memory.  Four resident CTAs of 40 KB keep the shared-memory carve-out at 164 KB, which leaves L1 the
+// ~90 KB it needs for the loads in flight: at 50 KB per CTA (carve-out 228 KB) a 2-D 1536^2 interpolator ran at
+// 40 Gpoints/s against 93 with the pack in global memory; at 33 KB staging wins, 118 against 95.
+constexpr unsigned kSmemLimit = 40u * 1024u;
 
 // Axis classification for the fast path: strictly increasing nodes (>= 2) may use it; evenly spaced
 // ones get a direct cell guess (cells per unit length), verified on the device against the real nodes.
@@ -278,28 +281,38 @@ int build_pack(nint_handle* h) {
         classify_axis(h, d, h->ax[d]);
         rec_bytes += align_up((unsigned)((h->axis_len[d] + 2) * 2 * es), 16);
     }
-    h->smem_axes = rec_bytes + 16ull * n <= kSmemLimit;
-    // Bucket tables: uniform axes only need them on the general path (1 bucket per cell); the others
-    // refine until (almost) every bucket narrows the bracket to two nodes, within the memory budget.
-    const unsigned long long budget = h->smem_axes ? kSmemLimit : (64ull << 20);
-    const unsigned long long soft = h->smem_axes ? kSmemPreferred : (64ull << 20);
+    unsigned long long smem_limit = kSmemLimit;
+    if (const char* env = std::getenv("NINT_SMEM_LIMIT")) smem_limit = std::strtoull(env, nullptr, 10);
+    // Bucket tables: uniform axes only need them on the general path (1 bucket per 8 cells); the others refine
+    // until (almost) every bucket narrows the bracket to two nodes, within the memory budget.  Returns false
+    // when the budget stopped the refinement of some axis early.
     std::vector<std::vector<uint2>> luts(n);
     unsigned long long lut_bytes = 0;
-    for (int d = 0; d < n; ++d) {
-        AxisMeta& a = h->ax[d];
-        const bool uniform = (a.flags & nint::kAxisUniform) != 0;
-        double per_cell = uniform ? 1.0 / 8 : 2.0;  // uniform axes: only the (rare) general path searches
-        // shrink first if even the starting table does not fit
-        while (per_cell > 1.0 / 64 && rec_bytes + lut_bytes + (unsigned long long)(per_cell * a.L) * 8 > budget) per_cell *= 0.5;
-        double wide = make_buckets(h, d, per_cell, a, luts[d]);
-        while (!uniform && wide > 0.002 && per_cell < 16.0) {
-            const unsigned long long next = rec_bytes + lut_bytes + (unsigned long long)(2 * per_cell * a.L) * 8;
-            if (next > soft) break;
-            per_cell *= 2.0;
-            wide = make_buckets(h, d, per_cell, a, luts[d]);
+    auto plan = [&](unsigned long long budget) {
+        bool refined = true;
+        lut_bytes = 0;
+        for (int d = 0; d < n; ++d) {
+            AxisMeta& a = h->ax[d];
+            const bool uniform = (a.flags & nint::kAxisUniform) != 0;
+            double per_cell = uniform ? 1.0 / 8 : 2.0;
+            // shrink first if even the starting table does not fit
+            while (per_cell > 1.0 / 64 && rec_bytes + lut_bytes + (unsigned long long)(per_cell * a.L) * 8 > budget) per_cell *= 0.5;
+            double wide = make_buckets(h, d, per_cell, a, luts[d]);
+            while (!uniform && wide > 0.002 && per_cell < 16.0) {
+                const unsigned long long next = rec_bytes + lut_bytes + (unsigned long long)(2 * per_cell * a.L) * 8;
+                if (next > budget) {
+                    refined = false;
+                    break;
+                }
+                per_cell *= 2.0;
+                wide = make_buckets(h, d, per_cell, a, luts[d]);
+            }
+            lut_bytes += align_up((unsigned)(a.M * 8), 16);
         }
-        lut_bytes += align_up((unsigned)(a.M * 8), 16);
-    }
+        return refined;
+    };
+    h->smem_axes = rec_bytes + 16ull * n <= smem_limit && plan(smem_limit) && rec_bytes + lut_bytes <= smem_limit;
+    if (!h->smem_axes) plan(64ull << 20);
     std::vector<unsigned char> pack;
     for (int d = 0; d < n; ++d) {
         AxisMeta& a = h->ax[d];

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--launches", type=int, default=3)
     ap.add_argument("--status", action="store_true")
     ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--extrap", default="", help="nd5: wrap (default) or fill")
     a = ap.parse_args()
     n = int(a.points)
     dev = torch.device("cuda", 0)
@@ -38,14 +39,15 @@ def main():
     elif a.case == "nd5":
         axes = [np.cumsum(rng.uniform(0.5, 1.5, 32)).astype(np.float32) for _ in range(5)]
         values = rng.uniform(0, 1, (32,) * 5).astype(np.float32)
-        g = nb.InterpND(axes, values, nb.strategy.Linear, nb.Extrapolate.Wrap, dtype=np.float32)
+        g = nb.InterpND(axes, values, nb.strategy.Linear, nb.Extrapolate.Fill(-1.0) if a.extrap == "fill" else nb.Extrapolate.Wrap, dtype=np.float32)
         cols = [(torch.rand(n, dtype=torch.float32, device=dev) * 1.5 - 0.25) * float(ax[-1] - ax[0]) + float(ax[0]) for ax in axes]
         tdt = torch.float32
     elif a.case == "2d":
-        axes = [np.arange(2048.0)] * 2
-        values = rng.uniform(0, 1, (2048, 2048))
+        G2 = a.grid if a.grid != 256 else 2048
+        axes = [np.arange(float(G2))] * 2
+        values = rng.uniform(0, 1, (G2, G2))
         g = nb.Interp2D(*axes, values, nb.strategy.Linear, nb.Extrapolate.Clamp)
-        cols = [torch.rand(n, dtype=torch.float64, device=dev) * 2047 * 1.1 - 0.05 * 2047 for _ in range(2)]
+        cols = [torch.rand(n, dtype=torch.float64, device=dev) * (G2 - 1) * 1.1 - 0.05 * (G2 - 1) for _ in range(2)]
         tdt = torch.float64
     else:
         gx = np.concatenate([[0.0], np.cumsum(rng.uniform(0.5, 1.5, 999))])
