@@ -757,7 +757,7 @@ __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_ke
 // Which mode a batch uses is decided on the device by order_probe_kernel from a sample of the batch; both kinds
 // of launch are always enqueued and the ones of the other mode return at once.
 // ---------------------------------------------------------------------------------------------
-constexpr int kSlabPer = 8;                   // points per lane and span
+constexpr int kSlabPer = 4;                   // points per lane and span (a larger list only costs L1: shared-memory carve-out)
 constexpr unsigned kSlabSpan = 32u * kSlabPer;  // points a warp scans at a time
 
 
