@@ -698,6 +698,17 @@ __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_ke
 #pragma unroll
             for (int d = 0; d < N; ++d) qn.v[d] = ld_stream(P.coords[d] + (size_t)in * P.coord_stride);
         }
+        // Nearest family: few instructions per point, so a trip is shorter than a DRAM round trip and one trip of
+        // look-ahead does not cover it.  The trip after the next starts its way to L2 (one request per 128-byte
+        // line, no register held): cell-ordered 3-D Nearest 146 -> 175 (f64), 177 -> 217 (f32) Gpoints/s.  Linear
+        // trips are long enough; there the extra requests cost 1-2 %.
+        if (STRAT != NINT_LINEAR) {
+            const unsigned i2 = in + stride;
+            if (i2 < n && (threadIdx.x & ((128u / (unsigned)sizeof(T)) - 1u)) == 0u) {
+#pragma unroll
+                for (int d = 0; d < N; ++d) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.coords[d] + (size_t)i2 * P.coord_stride));
+            }
+        }
 
         T p[N];
         bool oob = false;

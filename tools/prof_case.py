@@ -25,17 +25,23 @@ def main():
     ap.add_argument("--status", action="store_true")
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--extrap", default="", help="nd5: wrap (default) or fill")
+    ap.add_argument("--dtype", default="f64", help="random/sorted/nonuniform: f64 or f32")
+    ap.add_argument("--strategy", default="linear", help="random/sorted/nonuniform/1d: linear or nearest")
     a = ap.parse_args()
     n = int(a.points)
     dev = torch.device("cuda", 0)
     rng = np.random.default_rng(0)
     if a.case in ("random", "sorted", "nonuniform"):
         axes, values = bench.grid_and_values(uniform=a.case != "nonuniform", GRID=a.grid)
-        g = nb.Interp3D(*axes, values, nb.strategy.Linear, nb.Extrapolate.Error)
+        strat = nb.strategy.Nearest if a.strategy == "nearest" else nb.strategy.Linear
+        npdt = np.float32 if a.dtype == "f32" else np.float64
+        g = nb.Interp3D(*[ax.astype(npdt) for ax in axes], values.astype(npdt), strat, nb.Extrapolate.Error, dtype=npdt)
         cols = bench.gen_random(torch, n, dev, seed=1)
         if a.case == "sorted":
             bench.fill_cell_sorted(torch, cols, dev, seed=2, GRID=a.grid)
-        tdt = torch.float64
+        tdt = torch.float32 if a.dtype == "f32" else torch.float64
+        if a.dtype == "f32":
+            cols = [c.to(torch.float32).clamp_(0.0, 1.0) for c in cols]
     elif a.case == "nd5":
         axes = [np.cumsum(rng.uniform(0.5, 1.5, 32)).astype(np.float32) for _ in range(5)]
         values = rng.uniform(0, 1, (32,) * 5).astype(np.float32)
@@ -51,7 +57,7 @@ def main():
         tdt = torch.float64
     else:
         gx = np.concatenate([[0.0], np.cumsum(rng.uniform(0.5, 1.5, 999))])
-        g = nb.Interp1D(gx, rng.uniform(0, 1, 1000), nb.strategy.Linear, nb.Extrapolate.Error)
+        g = nb.Interp1D(gx, rng.uniform(0, 1, 1000), nb.strategy.Nearest if a.strategy == "nearest" else nb.strategy.Linear, nb.Extrapolate.Error)
         cols = [torch.rand(n, dtype=torch.float64, device=dev) * gx[-1]]
         tdt = torch.float64
     out = torch.empty(n, dtype=tdt, device=dev)
