@@ -127,7 +127,7 @@ struct nint_handle {
     nint_batch_info* d_info = nullptr;
     int* d_mode = nullptr;  // ring of query-order flags written by the order probe (one per batch call)
     std::atomic<unsigned> mode_slot{0};
-    int* last_mode = nullptr;  // flag of the most recent probed batch (diagnostics)
+    std::atomic<int*> last_mode{nullptr};  // flag of the most recent batch if it was probed (diagnostics)
     void* d_pt = nullptr;   // one point
     void* d_res = nullptr;  // one value + status byte
     Pipeline pipe;
@@ -533,14 +533,17 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     cfg.slab = 0;
     const int windows = slab_windows(h, n);
     if (windows <= 0) {
+        h->last_mode.store(nullptr, std::memory_order_relaxed);
         cudaError_t e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : nint::launch_fixed<T>(P, cfg);
         if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
         return NINT_OK;
     }
     // Large table, Linear: let the device decide from a sample of the batch whether the queries are coherent
     // (single pass on the cell-packed table) or not (slab passes on the plain table); enqueue both.
+    // a ring of 64 flags: calls on one stream run in order, so a slot is only reused early if more than 64 batch
+    // calls of this handle are in flight on different streams at once
     int* flag = h->d_mode + (h->mode_slot.fetch_add(1) & 63u);
-    h->last_mode = flag;
+    h->last_mode.store(flag, std::memory_order_relaxed);
     cudaError_t e = nint::launch_order_probe<T>(P, flag, stream);
     if (e != cudaSuccess) return cuda_fail(e, "order probe launch");
     P.mode_flag = flag;
@@ -1015,11 +1018,12 @@ int nint_host_free(void* ptr) {
 
 int nint_last_query_order(nint_handle* h) {
     if (!h) return fail(NINT_E_INVALID_ARGUMENT, -1, "handle is NULL");
-    if (!h->last_mode) return 0;
+    const int* flag = h->last_mode.load(std::memory_order_relaxed);
+    if (!flag) return 0;
     DeviceGuard guard(h->device);
     int v = 0;
     NINT_CUDA(cudaDeviceSynchronize());
-    NINT_CUDA(cudaMemcpy(&v, h->last_mode, sizeof v, cudaMemcpyDeviceToHost));
+    NINT_CUDA(cudaMemcpy(&v, flag, sizeof v, cudaMemcpyDeviceToHost));
     return v;
 }
 
