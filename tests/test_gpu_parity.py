@@ -307,3 +307,54 @@ def test_slab_passes_and_order_probe(monkeypatch):
     got, st, _ = gpu_eval(g, cols)
     assert_same(got, st, *o.eval(cols), "wrap stays single pass")
     assert _lib.lib().nint_last_query_order(g._h) == 0
+
+
+def test_concurrent_batches_on_one_handle(monkeypatch):
+    # include/ninterp_cuda.h: a handle is immutable during batch calls, so several host threads may evaluate
+    # batches on their own streams at once -- on the single-pass route and on the probed one (order flag ring)
+    import threading
+
+    import torch
+
+    from gpu_util import assert_same, make_pair
+
+    monkeypatch.setenv("NINT_SLAB_MIN_BYTES", "0")
+    monkeypatch.setenv("NINT_SLAB_MIN_POINTS", "0")
+    rng = np.random.default_rng(2024)
+    dev = torch.device("cuda", 0)
+    for passes in ("0", "3"):
+        monkeypatch.setenv("NINT_SLABS", passes)
+        axes = _axes(rng, (40, 9, 7), np.float64, "uniform")
+        values = rng.uniform(-1, 1, (40, 9, 7))
+        g, o = make_pair(FIXED, axes, values, LIN, ERROR, dtype=np.float64)
+        jobs = []
+        for t in range(6):
+            cols = _queries(rng, axes, 150_000 + 1000 * t, np.float64, 0.05)
+            if t % 2:  # every other batch is coherent: both kinds of launch are live at the same time
+                order = np.argsort(cols[0], kind="stable")
+                cols = [c[order] for c in cols]
+            jobs.append((cols, o.eval(cols, nthreads=O.max_threads())))
+        results = [None] * len(jobs)
+
+        def work(t):
+            s = torch.cuda.Stream(device=dev)
+            cols = [torch.from_numpy(c).to(dev) for c in jobs[t][0]]
+            torch.cuda.synchronize()
+            outs = []
+            for _ in range(5):
+                out = torch.empty(cols[0].numel(), dtype=torch.float64, device=dev)
+                st = torch.empty(cols[0].numel(), dtype=torch.uint8, device=dev)
+                g.interpolate_batch(cols, out=out, status=st, stream=s.cuda_stream)
+                outs.append((out, st))
+            s.synchronize()
+            results[t] = [(a.cpu().numpy(), b.cpu().numpy()) for a, b in outs]
+
+        threads = [threading.Thread(target=work, args=(t,)) for t in range(len(jobs))]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        for t, (cols, (want, st_want)) in enumerate(jobs):
+            assert results[t] is not None, f"thread {t} failed"
+            for got, st in results[t]:
+                assert_same(got, st, want, st_want, f"concurrent passes={passes} thread {t}")
