@@ -796,8 +796,13 @@ constexpr int kSlabPer = 4;                   // points per lane and span (a lar
 constexpr unsigned kSlabSpan = 32u * kSlabPer;  // points a warp scans at a time
 
 
+// Resident CTAs per SM for slab_kernel.  Unlike the single pass, this kernel keeps the scan state next to a whole
+// point evaluation: at 64 registers (4 CTAs) it spills 60-170 bytes per thread and runs at 28.1 Gpoints/s on the
+// headline workload; at 80 registers (3 CTAs, no spills) 32.7; at 96 (2 CTAs) 31.4; at 48 (5 CTAs) 25.6.
+constexpr int slab_ctas(int n, int elem_bytes) { return n <= 3 ? 3 : min_ctas(n, elem_bytes); }
+
 template <class T, int N, bool IS_ND, int PRE, bool UNI>
-__global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) slab_kernel(const __grid_constant__ Params<T> P) {
+__global__ void __launch_bounds__(kBlock, slab_ctas(N, (int)sizeof(T))) slab_kernel(const __grid_constant__ Params<T> P) {
     extern __shared__ __align__(16) unsigned char smem_pack[];
     __shared__ unsigned short s_list[kBlock / 32][kSlabSpan];
     __shared__ unsigned long long s_info[4];  // n_error, n_panic, first_error, first_panic
