@@ -52,14 +52,25 @@ def test_config3_interp3d_linear_256cubed():
     # "Interp3D Linear f64, 256^3 uniform grid" at 4e6 points, uniform and non-uniform axes
     rng = np.random.default_rng(3)
     v = rng.uniform(0, 1, (256, 256, 256))
+    from gpu_util import assert_same, expected_info, gpu_eval, make_pair
+
+    from ninterp_b200 import _lib
+
     for axes in ([np.arange(256) * (1.0 / 255)] * 3, [np.cumsum(rng.uniform(0.5, 1.5, 256)) for _ in range(3)]):
-        cols = [rng.uniform(a[0], a[-1], 4_000_000) for a in axes]
-        _, st = _run(0, axes, v, LIN, ERROR, cols)
-        assert (st == 0).all()
-        # cell-sorted order must give the same values as the unsorted batch
+        # 6e6 points: above the batch size from which a table of this size is routed by the order probe
+        cols = [rng.uniform(a[0], a[-1], 6_000_000) for a in axes]
+        g, o = make_pair(0, axes, v, LIN, ERROR, dtype=np.float64)
+        want, st_want = o.eval(cols, nthreads=O.max_threads())
+        got, st, info = gpu_eval(g, cols)
+        assert_same(got, st, want, st_want, "random order")
+        assert info == expected_info(st_want) and (st == 0).all()
+        assert _lib.lib().nint_last_query_order(g._h) == 2  # incoherent: slab passes over the plain table
+        # cell-sorted order must give the same values as the unsorted batch, through the single pass
         order = np.lexsort([np.searchsorted(axes[2], cols[2]), np.searchsorted(axes[1], cols[1]),
                             np.searchsorted(axes[0], cols[0])])
-        _run(0, axes, v, LIN, ERROR, [c[order] for c in cols])
+        got, st, info = gpu_eval(g, [c[order] for c in cols])
+        assert_same(got, st, want[order], st_want[order], "cell order")
+        assert _lib.lib().nint_last_query_order(g._h) == 1
 
 
 def test_config4_interpnd_f32_n5_wrap_fill():
