@@ -81,7 +81,7 @@ const char* extrap_name(int e) {
 
 struct AxisMeta {
     int L = 0, M = 0;
-    unsigned node_off = 0, lut_off = 0;
+    unsigned node_off = 0, lut_off = 0, guess_off = 0;
     double g0 = 0, gl = 0, inv_w = 0, inv_h = 0;
     int flags = 0;
     long long vstride = 0;
@@ -118,7 +118,8 @@ struct nint_handle {
     void* d_values = nullptr;
     void* d_cells = nullptr;  // cell-packed copy of the table for Linear (2^N corners per cell), or NULL
     unsigned char* d_pack = nullptr;
-    unsigned pack_bytes = 0;
+    unsigned pack_bytes = 0;      // whole pack in global memory
+    unsigned pack_hot_bytes = 0;  // leading part the kernels stage in shared memory: records and guess tables
     bool smem_axes = true;
     float l2_frac = 0.0f;  // share of the value table held evict_last in L2
     AxisMeta ax[NINT_MAX_NDIM];
@@ -185,11 +186,15 @@ unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
 // Bucket table of one axis.  Bucket b of width w_eff covers [g0 + b*w_eff, g0 + (b+1)*w_eff); a point
 // that the device maps to bucket b lies, with rounding, inside buckets b-1..b+1, so its node count
 // c = #{g < p} satisfies K[b-1] <= c <= K[b+2] where K[j] = #{g < edge j}.
-void build_lut(int dtype, const void* nodes, int L, int M, double g0, double inv_w_eff, std::vector<uint2>& lut) {
+// Returns the number of buckets with two or more nodes inside: there the fast path's two candidate cells do not
+// cover every point of the bucket.
+size_t build_lut(int dtype, const void* nodes, int L, int M, double g0, double inv_w_eff, std::vector<uint2>& lut,
+                 std::vector<unsigned>& guess) {
     lut.resize(M);
+    guess.assign(M, 0u);
     if (M == 1) {
         lut[0] = make_uint2(0u, (unsigned)L);
-        return;
+        return L > 2 ? 1 : 0;
     }
     // work with offsets from the first node, as the device does: (g - g0) is accurate to a relative
     // 2^-53 of the span, far below one bucket, whatever the magnitude of g0
@@ -197,6 +202,7 @@ void build_lut(int dtype, const void* nodes, int L, int M, double g0, double inv
     for (int i = 0; i < L; ++i) rel[i] = load_elem(dtype, nodes, i) - g0;
     const double w = 1.0 / inv_w_eff;
     std::vector<unsigned> K(M + 1);
+    size_t wide = 0;
     for (int j = 0; j <= M; ++j) {
         const double edge = (double)j * w;
         K[j] = (unsigned)(std::lower_bound(rel.begin(), rel.end(), edge) - rel.begin());
@@ -205,7 +211,13 @@ void build_lut(int dtype, const void* nodes, int L, int M, double g0, double inv
         const unsigned lo = (b == 0) ? 0u : K[b - 1];
         const unsigned hi = (b + 2 >= M) ? (unsigned)L : K[b + 2];
         lut[b] = make_uint2(lo, std::max(hi, lo));
+        // The fast path's guess: the cell that holds the bucket's left edge.  Only a hint -- the kernels verify
+        // g[k] < p <= g[k+1] against the nodes and try the next cell once before giving up.
+        const unsigned c = std::max(K[b], 1u) - 1u;
+        guess[b] = (unsigned)std::min<long long>((long long)c, std::max(0, L - 2));
+        wide += (K[b + 1] - K[b] >= 2u) ? 1 : 0;
     }
+    return wide;
 }
 
 // Axis packs up to this size are staged in shared memory by every CTA; larger ones are read through L1 from
@@ -250,9 +262,10 @@ void classify_axis(const nint_handle* h, int d, AxisMeta& a) {
     }
 }
 
-// Bucket table of axis d with `per_cell` buckets per cell.  Returns the share of buckets whose candidate
-// range is wider than the two nodes the fast path inspects.
-double make_buckets(const nint_handle* h, int d, double per_cell, AxisMeta& a, std::vector<uint2>& lut) {
+// Bucket tables of axis d with `per_cell` buckets per cell.  Returns the share of buckets that hold two or more
+// nodes (the fast path tries the guessed cell and the next one).
+double make_buckets(const nint_handle* h, int d, double per_cell, AxisMeta& a, std::vector<uint2>& lut,
+                    std::vector<unsigned>& guess) {
     const void* nodes = h->axes_host[d].data();
     const int L = a.L;
     int M = (int)std::min<double>(std::max(1.0, per_cell * (double)L), h->dtype == NINT_F64 ? 16777216.0 : 1048576.0);
@@ -267,9 +280,7 @@ double make_buckets(const nint_handle* h, int d, double per_cell, AxisMeta& a, s
     if (inv_w == 0.0) M = 1;  // degenerate axis: one bucket, plain binary search over all nodes
     a.M = M;
     a.inv_w = inv_w;
-    build_lut(h->dtype, nodes, L, M, a.g0, inv_w, lut);
-    size_t wide = 0;
-    for (const uint2& e : lut) wide += (e.y - e.x > 2u) ? 1 : 0;
+    const size_t wide = build_lut(h->dtype, nodes, L, M, a.g0, inv_w, lut, guess);
     return (double)wide / (double)M;
 }
 
@@ -283,35 +294,38 @@ int build_pack(nint_handle* h) {
     }
     unsigned long long smem_limit = kSmemLimit;
     if (const char* env = std::getenv("NINT_SMEM_LIMIT")) smem_limit = std::strtoull(env, nullptr, 10);
-    // Bucket tables: uniform axes only need them on the general path (1 bucket per 8 cells); the others refine
-    // until (almost) every bucket narrows the bracket to two nodes, within the memory budget.  Returns false
-    // when the budget stopped the refinement of some axis early.
+    // Bucket tables.  Every axis gets the {lo, hi} table the general path searches in (global memory only, 8 bytes
+    // per bucket); a non-uniform axis also gets the fast path's guess table (4 bytes per bucket), which is staged
+    // with the records.  Uniform axes guess by formula and only need a coarse {lo, hi} table (1 bucket per 8
+    // cells); the others refine until (almost) no bucket holds two nodes, within the budget of the staged part.
+    // Returns false when the budget stopped the refinement of some axis early.
     std::vector<std::vector<uint2>> luts(n);
-    unsigned long long lut_bytes = 0;
+    std::vector<std::vector<unsigned>> guesses(n);
+    unsigned long long guess_bytes = 0;
     auto plan = [&](unsigned long long budget) {
         bool refined = true;
-        lut_bytes = 0;
+        guess_bytes = 0;
         for (int d = 0; d < n; ++d) {
             AxisMeta& a = h->ax[d];
             const bool uniform = (a.flags & nint::kAxisUniform) != 0;
             double per_cell = uniform ? 1.0 / 8 : 2.0;
             // shrink first if even the starting table does not fit
-            while (per_cell > 1.0 / 64 && rec_bytes + lut_bytes + (unsigned long long)(per_cell * a.L) * 8 > budget) per_cell *= 0.5;
-            double wide = make_buckets(h, d, per_cell, a, luts[d]);
+            while (!uniform && per_cell > 1.0 / 64 && rec_bytes + guess_bytes + (unsigned long long)(per_cell * a.L) * 4 > budget) per_cell *= 0.5;
+            double wide = make_buckets(h, d, per_cell, a, luts[d], guesses[d]);
             while (!uniform && wide > 0.002 && per_cell < 16.0) {
-                const unsigned long long next = rec_bytes + lut_bytes + (unsigned long long)(2 * per_cell * a.L) * 8;
+                const unsigned long long next = rec_bytes + guess_bytes + (unsigned long long)(2 * per_cell * a.L) * 4;
                 if (next > budget) {
                     refined = false;
                     break;
                 }
                 per_cell *= 2.0;
-                wide = make_buckets(h, d, per_cell, a, luts[d]);
+                wide = make_buckets(h, d, per_cell, a, luts[d], guesses[d]);
             }
-            lut_bytes += align_up((unsigned)(a.M * 8), 16);
+            if (!uniform) guess_bytes += align_up((unsigned)(a.M * 4), 16);
         }
         return refined;
     };
-    h->smem_axes = rec_bytes + 16ull * n <= smem_limit && plan(smem_limit) && rec_bytes + lut_bytes <= smem_limit;
+    h->smem_axes = rec_bytes + 16ull * n <= smem_limit && plan(smem_limit) && rec_bytes + guess_bytes <= smem_limit;
     if (!h->smem_axes) plan(64ull << 20);
     std::vector<unsigned char> pack;
     for (int d = 0; d < n; ++d) {
@@ -346,13 +360,24 @@ int build_pack(nint_handle* h) {
                 std::memcpy(rec + es, &r, es);
             }
         }
+    }
+    for (int d = 0; d < n; ++d) {  // guess tables: the rest of the staged part
+        AxisMeta& a = h->ax[d];
+        a.guess_off = (unsigned)pack.size();
+        if (a.flags & nint::kAxisUniform) continue;
+        pack.resize(pack.size() + align_up((unsigned)(a.M * 4), 16), 0);
+        std::memcpy(pack.data() + a.guess_off, guesses[d].data(), (size_t)a.M * 4);
+    }
+    h->pack_hot_bytes = (unsigned)pack.size();
+    for (int d = 0; d < n; ++d) {  // {lo, hi} tables: read from global memory by the general path
+        AxisMeta& a = h->ax[d];
         a.lut_off = (unsigned)pack.size();
         pack.resize(pack.size() + align_up((unsigned)(a.M * 8), 16), 0);
         std::memcpy(pack.data() + a.lut_off, luts[d].data(), (size_t)a.M * 8);
     }
     h->pack_bytes = (unsigned)pack.size();
     if (h->pack_bytes == 0) return NINT_OK;
-    if (h->smem_axes && h->pack_bytes > 220u * 1024u) h->smem_axes = false;
+    if (h->smem_axes && h->pack_hot_bytes > 220u * 1024u) h->smem_axes = false;
     NINT_CUDA(cudaMalloc((void**)&h->d_pack, h->pack_bytes));
     NINT_CUDA(cudaMemcpy(h->d_pack, pack.data(), h->pack_bytes, cudaMemcpyHostToDevice));
     return NINT_OK;
@@ -453,7 +478,7 @@ void fill_params(const nint_handle* h, nint::Params<T>& P) {
     P.values = (const T*)h->d_values;
     P.cells = (h->strategy == NINT_LINEAR) ? (const T*)h->d_cells : nullptr;
     P.pack = h->d_pack;
-    P.pack_bytes = h->pack_bytes;
+    P.pack_bytes = h->pack_hot_bytes;
     P.fill = (T)h->fill;
     P.extrap = h->extrap;
     P.l2_frac = h->l2_frac;
@@ -463,6 +488,7 @@ void fill_params(const nint_handle* h, nint::Params<T>& P) {
         P.M[d] = a.M;
         P.node_off[d] = a.node_off;
         P.lut_off[d] = a.lut_off;
+        P.guess_off[d] = a.guess_off;
         P.vstride[d] = a.vstride;
         P.cstride[d] = a.cstride;
         P.g0[d] = (T)a.g0;
@@ -527,7 +553,7 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     cfg.all_uniform = 1;
     for (int d = 0; d < h->ndim_eff; ++d)
         if ((h->ax[d].flags & (nint::kAxisUniform | nint::kAxisFast)) != (nint::kAxisUniform | nint::kAxisFast)) cfg.all_uniform = 0;
-    cfg.smem_bytes = h->pack_bytes;
+    cfg.smem_bytes = h->pack_hot_bytes;
     cfg.sm_count = h->sm_count;
     cfg.stream = stream;
     cfg.slab = 0;

@@ -56,7 +56,7 @@ struct Params {
     const T* values;
     const T* cells;              // cell-packed copy of the table (2^N corners per cell, contiguous) or NULL
     const unsigned char* pack;   // axis pack in global memory
-    unsigned pack_bytes;         // multiple of 16
+    unsigned pack_bytes;         // multiple of 16: records + guess tables, the part staged in shared memory
     unsigned long long n;           // points in this launch: at most kMaxLaunchPoints (the host splits larger batches)
     unsigned long long index_base;  // batch index of point 0 (host pipeline chunks, split launches)
     T fill;
@@ -73,7 +73,8 @@ struct Params {
     int M[kMaxDim];
     int flags[kMaxDim];
     unsigned node_off[kMaxDim];  // byte offsets into the pack: {node, cell reciprocal} records
-    unsigned lut_off[kMaxDim];
+    unsigned lut_off[kMaxDim];   // {lo, hi} bucket tables: beyond pack_bytes, read from global memory only
+    unsigned guess_off[kMaxDim]; // guess tables of the non-uniform axes (inside pack_bytes)
     long long vstride[kMaxDim];  // element strides of `values`
     long long cstride[kMaxDim];  // cell strides of `cells` (in cells)
     T g0[kMaxDim], gl[kMaxDim];
@@ -85,7 +86,8 @@ template <class T>
 struct AxisRef {
     const T* rec;      // L+2 records {node, rcp}: rec[2l] = g[l] (two +inf pads at the end),
                        // rec[2l+1] = RN(1 / (g[l+1] - g[l])) for cells inside the safe exponent window, else 0
-    const uint2* lut;  // bucket b -> [lo, hi]: bounds on the node count below any point of the bucket
+    const uint2* lut;  // bucket b -> [lo, hi]: bounds on the node count below any point of the bucket (global memory)
+    const unsigned* guess;  // bucket b -> the cell holding the bucket's left edge (non-uniform axes)
     int L, M, flags;
     T g0, gl, inv_w, inv_h;
     __device__ __forceinline__ T g(int i) const { return rec[2 * i]; }
@@ -275,7 +277,8 @@ template <class T>
 __device__ __forceinline__ AxisRef<T> load_axis(const Params<T>& P, const unsigned char* pack, int d) {
     AxisRef<T> a;
     a.rec = reinterpret_cast<const T*>(pack + P.node_off[d]);
-    a.lut = reinterpret_cast<const uint2*>(pack + P.lut_off[d]);
+    a.lut = reinterpret_cast<const uint2*>(P.pack + P.lut_off[d]);
+    a.guess = reinterpret_cast<const unsigned*>(pack + P.guess_off[d]);
     a.L = P.L[d];
     a.M = P.M[d];
     a.flags = P.flags[d];
@@ -521,15 +524,11 @@ __device__ __forceinline__ bool guess_cell(const AxisRef<T>& a, T p, int& k) {
     if (a.flags & kAxisUniform) {
         k = to_int_sat((p - a.g0) * a.inv_h);
     } else {
+        // the cell of the bucket's left edge (already inside [0, L-2]); verify_*_retry() settles whether the point
+        // is in it, in the next one, or needs the general path
         int b = to_int_sat((p - a.g0) * a.inv_w);
         b = max(0, min(b, a.M - 1));
-        const uint2 e = a.lut[b];
-        const int lo = (int)e.x;
-        ok = ok && ((int)e.y - lo <= 2);
-        // nodes at or beyond the upper bound are >= p and the two pads are +inf: count two unconditionally
-        const T n0 = a.g(lo);
-        const T n1 = a.g(lo + 1);
-        k = lo + (n0 < p ? 1 : 0) + (n1 < p ? 1 : 0) - 1;
+        k = (int)a.guess[b];
     }
     k = max(0, min(k, a.L - 2));
     return ok;
@@ -569,6 +568,32 @@ __device__ __forceinline__ bool verify_cell_linear(const AxisRef<T>& ax, T p, in
     return (in_div_window_pos(a) || first) && (p <= G1);
 }
 
+// A non-uniform axis guesses the cell that holds its bucket's left edge, so the point may also sit in the next cell
+// (buckets are narrower than almost every cell): one retry there, for the lanes that need it, before the general
+// path.  Uniform axes guess by formula and are right or on a node.
+template <class T, bool STRICT, bool FIRST, bool UNI>
+__device__ __forceinline__ bool verify_linear_retry(const AxisRef<T>& ax, T p, int& k, T& a, T& w, T& R) {
+    bool ok = verify_cell_linear<T, STRICT, FIRST>(ax, p, k, a, w, R);
+    if (!UNI) {
+        if (!ok && !(ax.flags & kAxisUniform) && k < ax.L - 2 && p > ax.g(k + 1)) {
+            ++k;
+            ok = verify_cell_linear<T, STRICT, FIRST>(ax, p, k, a, w, R);
+        }
+    }
+    return ok;
+}
+template <class T, bool STRICT, bool UNI>
+__device__ __forceinline__ bool verify_retry(const AxisRef<T>& ax, T p, int& k, T& G0, T& G1, T& R) {
+    bool ok = verify_cell<T, STRICT>(ax, p, k, G0, G1, R);
+    if (!UNI) {
+        if (!ok && !(ax.flags & kAxisUniform) && k < ax.L - 2 && p > G1) {
+            ++k;
+            ok = verify_cell<T, STRICT>(ax, p, k, G0, G1, R);
+        }
+    }
+    return ok;
+}
+
 // The whole fast path for one point; false when anything about it needs the general path.
 template <class T, int N, bool IS_ND, int STRAT, bool UNI, bool FIRST, bool PLAIN = false>
 __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned char* pack, unsigned long long pol,
@@ -588,7 +613,7 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
 #pragma unroll
         for (int d = 0; d < N; ++d) {
             T a, w, r;
-            ok = verify_cell_linear<T, kCollapse, FIRST>(load_axis<T>(P, pack, d), p[d], k[d], a, w, r) && ok;
+            ok = verify_linear_retry<T, kCollapse, FIRST, UNI>(load_axis<T>(P, pack, d), p[d], k[d], a, w, r) && ok;
             t[d] = div_markstein<T>(a, w, r);
         }
         // N >= 4: no speculative gather for a point that is going to the general path anyway; with mostly
@@ -629,7 +654,7 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
 #pragma unroll
         for (int d = 0; d < N; ++d) {
             T G0, G1, r;
-            ok = verify_cell<T, kCollapse>(load_axis<T>(P, pack, d), p[d], k[d], G0, G1, r) && ok;
+            ok = verify_retry<T, kCollapse, UNI>(load_axis<T>(P, pack, d), p[d], k[d], G0, G1, r) && ok;
             int idx = k[d];
             if (STRAT == NINT_NEAREST) idx += ((p[d] - G0) < (G1 - p[d])) ? 0 : 1;  // tie -> upper (three/strategies.rs:70-74)
             if (STRAT == NINT_RIGHT_NEAREST) idx += 1;

@@ -56,7 +56,7 @@ def main():
         cols = [torch.rand(n, dtype=torch.float64, device=dev) * (G2 - 1) * 1.1 - 0.05 * (G2 - 1) for _ in range(2)]
         tdt = torch.float64
     else:
-        gx = np.concatenate([[0.0], np.cumsum(rng.uniform(0.5, 1.5, 999))])
+        gx = np.concatenate([[0.0], np.cumsum(rng.uniform(0.5, 1.5, 999))]) if a.case == "1d" else np.arange(1000.0)
         g = nb.Interp1D(gx, rng.uniform(0, 1, 1000), nb.strategy.Nearest if a.strategy == "nearest" else nb.strategy.Linear, nb.Extrapolate.Error)
         cols = [torch.rand(n, dtype=torch.float64, device=dev) * gx[-1]]
         tdt = torch.float64
