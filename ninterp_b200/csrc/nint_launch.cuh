@@ -40,8 +40,8 @@ cudaError_t launch_variant(const Params<T>& P, const LaunchCfg& cfg) {
 // interpolators whose axes are all uniform (no bucket tables, no per-axis flags in the point loop).
 template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE>
 cudaError_t launch_uni(const Params<T>& P, const LaunchCfg& cfg) {
-    if (SMEM && cfg.all_uniform && (STRAT != NINT_LINEAR || P.cells != nullptr))
-        return launch_variant<T, N, IS_ND, STRAT, SMEM, PRE, SMEM>(P, cfg);
+    if (cfg.all_uniform && (STRAT != NINT_LINEAR || P.cells != nullptr))
+        return launch_variant<T, N, IS_ND, STRAT, SMEM, PRE, true>(P, cfg);
     return launch_variant<T, N, IS_ND, STRAT, SMEM, PRE, false>(P, cfg);
 }
 template <class T, int N, bool IS_ND, int STRAT, bool SMEM>
