@@ -1,5 +1,5 @@
 // nint_api.cu — the C ABI of include/ninterp_cuda.h: handle life cycle, the reference's
-// validation rules, the axis pack (nodes + bucket tables) and the host-buffer pipeline.
+// validation rules, the axis pack (node records, guess tables, bucket bounds) and the host-buffer pipeline.
 //
 // Reference items mirrored here (paths relative to the reference's src/):
 //   InterpData::validate       interpolator/data.rs:69-89

@@ -13,14 +13,15 @@
 //               computing the weights, gather the cell, blend.  A verified cell implies the point is in
 //               range and finite, so the fast path is the same for every Extrapolate policy.
 //   general     everything else (out of range, NaN/inf, exact node hits, degenerate axes, duplicate
-//               nodes, wide buckets): an out-of-line restatement of the reference's control flow.
+//               nodes, buckets holding several nodes): an out-of-line restatement of the reference's control flow.
 //
 // Data layout in HBM
 //   coords   struct of arrays (one column per axis) or array of [T;N] points (coord_stride)
 //   values   dense C-order table, last axis fastest
 //   cells    optional cell-packed copy for Linear: the 2^N corners of each cell contiguous and aligned
-//   pack     per axis: L nodes (+2 pads), an M-entry bucket table, L cell reciprocals; staged once per
-//            CTA in shared memory so the bracket search never leaves the SM
+//   pack     per axis: L+2 records {node, cell reciprocal} and, for a non-uniform axis, an M-entry guess table
+//            (bucket -> cell); staged once per CTA in shared memory when small enough.  Behind them, in global
+//            memory only, the {lo, hi} bucket tables the general path searches in
 #pragma once
 #include <cuda_runtime.h>
 
@@ -78,7 +79,7 @@ struct Params {
     long long vstride[kMaxDim];  // element strides of `values`
     long long cstride[kMaxDim];  // cell strides of `cells` (in cells)
     T g0[kMaxDim], gl[kMaxDim];
-    T inv_w[kMaxDim];            // buckets per unit length (bucket table)
+    T inv_w[kMaxDim];            // buckets per unit length (guess table and {lo, hi} table share the buckets)
     T inv_h[kMaxDim];            // cells per unit length (uniform axes)
 };
 

@@ -37,7 +37,8 @@ cudaError_t launch_variant(const Params<T>& P, const LaunchCfg& cfg) {
 }
 
 // Clamp and Wrap enter the fast path (clamp first / wrap and retry), so they select their own kernels; so do
-// interpolators whose axes are all uniform (no bucket tables, no per-axis flags in the point loop).
+// interpolators whose axes are all uniform (no guess tables, no per-axis flags in the point loop), wherever
+// their axis pack lives.
 template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE>
 cudaError_t launch_uni(const Params<T>& P, const LaunchCfg& cfg) {
     if (cfg.all_uniform && (STRAT != NINT_LINEAR || P.cells != nullptr))
