@@ -30,6 +30,33 @@ def test_library_exports_every_declared_symbol():
     assert b"ninterp" in lib.nint_version()
 
 
+def test_rust_sys_crate_declares_the_same_abi():
+    # integration/rust/ninterp-cuda-sys is source only (no Rust toolchain in this image): at least keep it in step
+    # with the header -- same functions in the same order, same argument counts, same enum values
+    header = (ROOT / "include" / "ninterp_cuda.h").read_text()
+    rust = (ROOT / "integration" / "rust" / "ninterp-cuda-sys" / "src" / "lib.rs").read_text()
+    rust_fns = re.findall(r"pub fn (nint_\w+)\s*\(([^)]*)\)", rust, flags=re.S)
+    assert [n for n, _ in rust_fns] == _declared()
+    for name, rust_args in rust_fns:
+        c_args = re.search(r"\b%s\s*\(([^)]*)\)" % name, header, flags=re.S).group(1)
+        n_c = 0 if c_args.strip() in ("", "void") else c_args.count(",") + 1
+        n_rust = len([a for a in rust_args.split(",") if a.strip()])
+        assert n_c == n_rust, f"{name}: {n_c} arguments in C, {n_rust} in Rust"
+    enum_values = dict(re.findall(r"\b(NINT_[A-Z0-9_]+)\s*=\s*(-?\d+)", header))
+    rust_consts = dict(re.findall(r"pub const (NINT_[A-Z0-9_]+): c_int = (-?\d+);", rust))
+    assert enum_values and set(enum_values) <= set(rust_consts)
+    for k, v in enum_values.items():
+        assert rust_consts[k] == v, k
+    # INTEGRATION.md quotes the same extern block, and the wrapper module verbatim
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    for name, _ in rust_fns:
+        assert f"pub fn {name}(" in doc, f"{name} is missing from INTEGRATION.md"
+    sec2 = doc[doc.index("## 2. The batch method"):doc.index("## 3. What maps to what")]
+    quoted = "".join(re.findall(r"```rust\n(.*?)```", sec2, flags=re.S))
+    wrapper = (ROOT / "integration" / "rust" / "ninterp" / "src" / "cuda.rs").read_text()
+    assert wrapper.endswith(quoted) and len(quoted) > 2000
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
 
