@@ -128,6 +128,11 @@ class _InterpBase:
         self.strategy = strategy  # the reference assigns before checking
         check(L.lib().nint_set_strategy(self._h, strategy.code))
 
+    def last_query_order(self) -> int:
+        """Diagnostics: route of the most recent batch (0 no order probe ran, 1 coherent: single pass on the
+        cell-packed table, 2 incoherent: slab passes on the plain table).  Synchronises the device."""
+        return int(L.lib().nint_last_query_order(self._h))
+
     # -- batch entry points (new) ----------------------------------------------------------------
     def interpolate_batch(self, coords, out=None, status=None, info=None, stream=None):
         """Evaluate points resident on this interpolator's GPU (torch CUDA tensors).
