@@ -119,6 +119,7 @@ extern "C" {
     ) -> c_int;
     pub fn nint_interpolate(h: *mut nint_handle, point: *const c_void, point_len: usize, out: *mut c_void) -> c_int;
     pub fn nint_last_query_order(h: *mut nint_handle) -> c_int;
+    pub fn nint_last_incoherent_route(h: *mut nint_handle) -> c_int;
     pub fn nint_host_alloc(ptr: *mut *mut c_void, bytes: usize) -> c_int;
     pub fn nint_host_free(ptr: *mut c_void) -> c_int;
     pub fn nint_last_error_message() -> *const c_char;

@@ -28,7 +28,7 @@ SYMBOLS = [
     "nint_create", "nint_destroy", "nint_ndim", "nint_validate", "nint_set_extrapolate", "nint_set_strategy",
     "nint_interpolate_batch", "nint_interpolate_batch_aos", "nint_interpolate_batch_host", "nint_interpolate_batch_host_multi", "nint_interpolate",
     "nint_host_alloc", "nint_host_free", "nint_last_error_message", "nint_last_error_dim", "nint_version",
-    "nint_launch_count", "nint_selftest_divide", "nint_last_query_order",
+    "nint_launch_count", "nint_selftest_divide", "nint_last_query_order", "nint_last_incoherent_route",
 ]
 
 
@@ -71,6 +71,7 @@ def lib() -> C.CDLL:
     L.nint_version.restype = C.c_char_p
     L.nint_launch_count.restype = C.c_uint64
     L.nint_last_query_order.argtypes = [vp]
+    L.nint_last_incoherent_route.argtypes = [vp]
     L.nint_selftest_divide.argtypes = [i32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     _lib = L
     return L

@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 OBJ = PKG / "_build"
 SO = PKG / "libninterp_cuda.so"
 
-SOURCES = ["nint_api.cu", "nint_fixed_f64.cu", "nint_fixed_f32.cu", "nint_nd_f64.cu", "nint_nd_f32.cu", "nint_selftest.cu"]
+SOURCES = ["nint_api.cu", "nint_fixed_f64.cu", "nint_fixed_f32.cu", "nint_nd_f64.cu", "nint_nd_f32.cu", "nint_tile_f64.cu", "nint_tile_f32.cu", "nint_selftest.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -19,7 +19,7 @@
 #include <thread>
 #include <vector>
 
-#include "nint_device.cuh"
+#include "nint_tile.cuh"
 
 namespace nint {
 std::atomic<unsigned long long> g_launch_count{0};
@@ -126,9 +126,17 @@ struct nint_handle {
     int sm_count = 0;
     // scratch for the synchronous entry points
     nint_batch_info* d_info = nullptr;
-    int* d_mode = nullptr;  // ring of query-order flags written by the order probe (one per batch call)
+    nint::ProbeSlot* d_probe = nullptr;  // ring of order-probe slots (verdict + scratch), one per batch call
     std::atomic<unsigned> mode_slot{0};
-    std::atomic<int*> last_mode{nullptr};  // flag of the most recent batch if it was probed (diagnostics)
+    std::atomic<const int*> last_mode{nullptr};  // verdict of the most recent batch if it was probed (diagnostics)
+    std::atomic<int> last_route{0};              // what was enqueued for an incoherent verdict: 0 none, 1 slab passes, 2 binned tiles
+    int probe_shift = 3;                         // log2(cells per coarse tile and axis) of the order probe
+    unsigned probe_max_distinct = 0;             // coherent when the windows' mean footprint is at most this many coarse tiles
+    // binned route (nint_tile.cuh): tile geometry, TMA descriptor of the plain table, pool for the per-call lists
+    bool tile_ready = false;
+    nint::TileGeom tile_geom{};
+    CUtensorMap tile_map{};
+    cudaMemPool_t pool = nullptr;
     void* d_pt = nullptr;   // one point
     void* d_res = nullptr;  // one value + status byte
     Pipeline pipe;
@@ -528,6 +536,181 @@ int slab_windows(const nint_handle* h, size_t n) {
     return w;
 }
 
+// ------------------------------------------------------------------------------- binned route (nint_tile.cuh)
+// Whether an incoherent batch of n points goes through the binned tiles.  Same regime as the slab passes (Linear,
+// 3-D, a table the single pass cannot keep in L2, a batch large enough to pay for streaming the table once per
+// superchunk); Wrap is fine here because the lists hold weights, not coordinates.  NINT_ROUTE=slab|tile|single
+// overrides (tests, measurements); NINT_SLABS=k > 0 keeps forcing slab passes, NINT_SLABS=0 the single pass.
+bool tile_route(const nint_handle* h, size_t n, int windows) {
+    if (!h->tile_ready || h->constant || h->strategy != NINT_LINEAR || !h->smem_axes) return false;
+    const char* route = std::getenv("NINT_ROUTE");
+    const char* e_on = std::getenv("NINT_SLABS");
+    if (route && (!std::strcmp(route, "slab") || !std::strcmp(route, "single"))) return false;
+    if (e_on && !(route && !std::strcmp(route, "tile"))) return false;  // NINT_SLABS=k pins the older routes
+    for (int d = 0; d < 3; ++d)
+        if (!(h->ax[d].flags & nint::kAxisFast)) return false;
+    const char* e_bytes = std::getenv("NINT_SLAB_MIN_BYTES");
+    const char* e_points = std::getenv("NINT_SLAB_MIN_POINTS");
+    const long long min_bytes = e_bytes ? std::atoll(e_bytes) : 256ll << 20;
+    const long long min_points = e_points ? std::atoll(e_points) : 1ll << 22;
+    if ((long long)n < min_points) return false;
+    const double plain = (double)h->values_len * (double)elem_size(h->dtype);
+    const double single = h->d_cells ? plain * 8.0 : plain;
+    if (single < (double)min_bytes) return false;
+    // every superchunk streams the table once: beyond ~40 bytes per point of that the slab passes or the single
+    // pass are the better deal
+    const double per_point = plain * 1.2 / (double)(1ull << h->tile_geom.sc_shift);
+    if (!(route && !std::strcmp(route, "tile")) && per_point > 48.0) return false;
+    (void)windows;
+    return true;
+}
+
+// TMA descriptor of the plain table and the tile geometry.  Not an error when it cannot be built (strides that are
+// not 16-byte multiples, no driver entry point): the route is simply not offered.
+void build_tile(nint_handle* h) {
+    h->tile_ready = false;
+    if (h->constant || h->ndim_eff != 3 || h->strategy != NINT_LINEAR) return;
+    const size_t es = elem_size(h->dtype);
+    const size_t L0 = h->axis_len[0], L1 = h->axis_len[1], L2 = h->axis_len[2];
+    if (L0 < 2 || L1 < 2 || L2 < 2) return;
+    if ((L2 * es) % 16 != 0) return;  // cuTensorMapEncodeTiled: global strides are multiples of 16 bytes
+    nint::TileGeom& g = h->tile_geom;
+    g = nint::TileGeom{};
+    // cells per tile: 16 x 16 x 32 doubles (17 x 17 x 34 staged, 78.6 KB) or 16 x 32 x 32 floats (80.8 KB): two
+    // buffers fill one SM's shared memory
+    g.sh[0] = 4;
+    g.sh[1] = (es == 8) ? 4 : 5;
+    g.sh[2] = 5;
+    unsigned long long ntiles = 1, vol = 1;
+    for (int d = 0; d < 3; ++d) {
+        const int cells = (int)h->axis_len[d] - 1;
+        g.nt[d] = (cells + (1 << g.sh[d]) - 1) >> g.sh[d];
+        g.box[d] = (1 << g.sh[d]) + 1;
+        ntiles *= (unsigned long long)g.nt[d];
+    }
+    const int inner_q = (int)(16 / es);
+    g.box[2] = (g.box[2] + inner_q - 1) / inner_q * inner_q;
+    for (int d = 0; d < 3; ++d) vol *= (unsigned long long)g.box[d];
+    if (ntiles > (1ull << 20)) return;
+    g.ntiles = (int)ntiles;
+    g.tile_bytes = (unsigned)(vol * es);
+    g.buf_bytes = (g.tile_bytes + 127u) & ~127u;
+    unsigned sc_shift = 23;
+    if (const char* env = std::getenv("NINT_TILE_SC_SHIFT")) sc_shift = (unsigned)std::atoi(env);
+    g.sc_shift = std::min(28u, std::max(10u, sc_shift));
+    const unsigned long long per_list = (1ull << g.sc_shift) / ntiles;
+    g.cap = (unsigned)((per_list + per_list / 4 + 256 + 31) / 32 * 32);
+
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    const cuuint64_t gdim[3] = {L2, L1, L0};
+    const cuuint64_t gstride[2] = {L2 * es, L1 * L2 * es};
+    const cuuint32_t box[3] = {(cuuint32_t)g.box[2], (cuuint32_t)g.box[1], (cuuint32_t)g.box[0]};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = ((EncodeFn)fn)(&h->tile_map, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                                      h->d_values, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return;
+    if (!h->pool) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = h->device;
+        if (cudaMemPoolCreate(&h->pool, &props) != cudaSuccess) {
+            cudaGetLastError();
+            h->pool = nullptr;
+            return;
+        }
+        unsigned long long keep = ~0ull;  // the lists are the same size call after call: keep them in the pool
+        cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    h->tile_ready = true;
+}
+
+// Footprint bound of the order probe: the number of coarse tiles (8 cells per axis) of the table the single pass
+// gathers from that fit 48 MiB of L2, turned into the distinct-tile count 4096 points drawn from that many tiles show.
+void probe_threshold(nint_handle* h) {
+    h->probe_shift = 3;
+    if (const char* env = std::getenv("NINT_PROBE_SHIFT")) h->probe_shift = std::max(0, std::min(8, std::atoi(env)));
+    if (const char* env = std::getenv("NINT_PROBE_MAX_DISTINCT")) {
+        h->probe_max_distinct = (unsigned)std::atoi(env);
+        return;
+    }
+    double cells = 1.0;
+    for (int d = 0; d < h->ndim_eff; ++d) cells *= (double)std::min<size_t>((size_t)1 << h->probe_shift, std::max<size_t>(h->axis_len[d], 2) - 1);
+    const double corner = (h->strategy == NINT_LINEAR && h->d_cells) ? (double)(1u << h->ndim_eff) : 1.0;
+    const double tile_bytes = cells * corner * (double)elem_size(h->dtype);
+    const double r_max = std::max(1.0, 48.0 * 1024 * 1024 / tile_bytes);
+    const double d = r_max * (1.0 - std::exp(-(double)nint::kProbeWindowPts / r_max));
+    h->probe_max_distinct = (unsigned)std::max(1.0, std::floor(d));
+}
+
+// Enqueues bin + evaluate for the whole launch, in segments whose lists fit the scratch budget.
+// NINT_E_UNSUPPORTED: no memory for the lists (nothing was enqueued for the incoherent verdict yet).
+template <class T>
+int launch_tiles(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, cudaStream_t stream) {
+    nint::TileGeom G = h->tile_geom;
+    unsigned seg_shift = 28;
+    if (const char* env = std::getenv("NINT_TILE_SEG_SHIFT")) seg_shift = (unsigned)std::atoi(env);
+    seg_shift = std::min(30u, std::max(G.sc_shift, seg_shift));
+    const unsigned long long seg = 1ull << seg_shift;
+    const unsigned long long n = P.n;
+    const unsigned max_sc = (unsigned)((std::min(n, seg) + (1ull << G.sc_shift) - 1) >> G.sc_shift);
+    const size_t cursor_bytes = (size_t)max_sc * (size_t)G.ntiles * nint::kCursorStride * sizeof(unsigned);
+    const size_t record_bytes = (size_t)max_sc * (size_t)G.ntiles * (size_t)G.cap * nint::kTileRecBytes;
+    unsigned char* scratch = nullptr;
+    if (cudaMallocFromPoolAsync((void**)&scratch, cursor_bytes + record_bytes + 256, h->pool, stream) != cudaSuccess) {
+        cudaGetLastError();
+        return NINT_E_UNSUPPORTED;
+    }
+    G.cursor = (unsigned*)scratch;
+    G.records = scratch + ((cursor_bytes + 255) & ~(size_t)255);
+    nint::TileLaunch tl;
+    tl.is_nd = cfg.is_nd;
+    tl.all_uniform = cfg.all_uniform;
+    tl.sm_count = cfg.sm_count;
+    tl.smem_bytes = cfg.smem_bytes;
+    tl.stream = stream;
+    const size_t es = sizeof(T);
+    const T* cols0[3] = {P.coords[0], P.coords[1], P.coords[2]};
+    T* out0 = P.out;
+    uint8_t* st0 = P.status;
+    const unsigned long long base0 = P.index_base;
+    int rc = NINT_OK;
+    for (unsigned long long start = 0; start < n && rc == NINT_OK; start += seg) {
+        const unsigned long long m = std::min(seg, n - start);
+        for (int d = 0; d < 3; ++d) P.coords[d] = cols0[d] + start * P.coord_stride;
+        P.out = out0 + start;
+        P.status = st0 ? st0 + start : nullptr;
+        P.n = m;
+        P.index_base = base0 + start;
+        G.n_sc = (unsigned)((m + (1ull << G.sc_shift) - 1) >> G.sc_shift);
+        cudaError_t e = cudaMemsetAsync(G.cursor, 0, (size_t)G.n_sc * (size_t)G.ntiles * nint::kCursorStride * sizeof(unsigned), stream);
+        if (e == cudaSuccess) e = nint::launch_tile_bin<T>(P, G, tl);
+        if (e == cudaSuccess) {
+            nint::TileEval<T> E;
+            E.out = P.out;
+            E.mode_flag = P.mode_flag;
+            E.mode_want = P.mode_want;
+            e = nint::launch_tile_eval<T>(h->tile_map, E, G, tl);
+        }
+        if (e != cudaSuccess) rc = cuda_fail(e, "binned route launch");
+    }
+    (void)es;
+    cudaFreeAsync(scratch, stream);
+    return rc;
+}
+
 template <class T>
 int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride, size_t n, void* out,
                  uint8_t* status, nint_batch_info* info_dev, unsigned long long index_base, cudaStream_t stream) {
@@ -557,26 +740,44 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     cfg.sm_count = h->sm_count;
     cfg.stream = stream;
     cfg.slab = 0;
-    const int windows = slab_windows(h, n);
-    if (windows <= 0) {
+    int windows = slab_windows(h, n);
+    const bool tile = tile_route(h, n, windows);
+    h->last_route.store(0, std::memory_order_relaxed);
+    if (windows <= 0 && !tile) {
         h->last_mode.store(nullptr, std::memory_order_relaxed);
         cudaError_t e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : nint::launch_fixed<T>(P, cfg);
         if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
         return NINT_OK;
     }
-    // Large table, Linear: let the device decide from a sample of the batch whether the queries are coherent
-    // (single pass on the cell-packed table) or not (slab passes on the plain table); enqueue both.
-    // a ring of 64 flags: calls on one stream run in order, so a slot is only reused early if more than 64 batch
-    // calls of this handle are in flight on different streams at once
-    int* flag = h->d_mode + (h->mode_slot.fetch_add(1) & 63u);
+    // Large table, Linear: the device decides from windows of the batch whether the queries are coherent (single
+    // pass on the cell-packed table) or not (binned tiles, or slab passes on the plain table); both are enqueued.
+    // A ring of 64 probe slots: calls on one stream run in order, so a slot is only reused early if more than 64
+    // batch calls of this handle are in flight on different streams at once.
+    nint::ProbeSlot* slot = h->d_probe + (h->mode_slot.fetch_add(1) & 63u);
+    const int* flag = &slot->mode;
     h->last_mode.store(flag, std::memory_order_relaxed);
-    cudaError_t e = nint::launch_order_probe<T>(P, flag, stream);
+    cudaError_t e = nint::launch_order_probe2<T>(P, h->ndim_eff, h->probe_shift, h->probe_max_distinct * (unsigned)nint::kProbeWindows, slot, stream);
     if (e != cudaSuccess) return cuda_fail(e, "order probe launch");
     P.mode_flag = flag;
     P.mode_want = nint::kModeCoherent;
     e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : nint::launch_fixed<T>(P, cfg);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     P.mode_want = nint::kModeRandom;
+    if (tile) {
+        const int rc = launch_tiles<T>(h, P, cfg, stream);
+        if (rc == NINT_OK) {
+            h->last_route.store(2, std::memory_order_relaxed);
+            return NINT_OK;
+        }
+        if (rc != NINT_E_UNSUPPORTED) return rc;
+        if (windows <= 0) {  // no memory for the lists and no slab passes for this interpolator: the single pass takes both verdicts
+            cfg.slab = 0;
+            e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : nint::launch_fixed<T>(P, cfg);
+            if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+            return NINT_OK;
+        }
+    }
+    h->last_route.store(1, std::memory_order_relaxed);
     cfg.slab = 1;
     const int cells0 = (int)h->axis_len[0] - 1;
     const int per = (cells0 + windows - 1) / windows;
@@ -763,9 +964,12 @@ int nint_create(int device, int kind, int dtype, int ngrid, const size_t* axis_l
     if (rc == NINT_OK && !h->constant) rc = build_pack(h);
     if (rc == NINT_OK) rc = build_cells(h);
     if (rc == NINT_OK) {
+        build_tile(h);
+        probe_threshold(h);
         cudaError_t e2 = cudaMalloc((void**)&h->d_info, sizeof(nint_batch_info));
         if (e2 == cudaSuccess) e2 = cudaMalloc(&h->d_pt, NINT_MAX_NDIM * sizeof(double));
-        if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&h->d_mode, 64 * sizeof(int));
+        if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&h->d_probe, 64 * sizeof(nint::ProbeSlot));
+        if (e2 == cudaSuccess) e2 = cudaMemset(h->d_probe, 0, 64 * sizeof(nint::ProbeSlot));
         if (e2 == cudaSuccess) e2 = cudaMalloc(&h->d_res, 16);
         if (e2 != cudaSuccess) rc = cuda_fail(e2, "cudaMalloc");
     }
@@ -786,7 +990,8 @@ void nint_destroy(nint_handle* h) {
         if (h->d_cells) cudaFree(h->d_cells);
         if (h->d_pack) cudaFree(h->d_pack);
         if (h->d_info) cudaFree(h->d_info);
-        if (h->d_mode) cudaFree(h->d_mode);
+        if (h->d_probe) cudaFree(h->d_probe);
+        if (h->pool) cudaMemPoolDestroy(h->pool);
         if (h->d_pt) cudaFree(h->d_pt);
         if (h->d_res) cudaFree(h->d_res);
     }
@@ -829,6 +1034,13 @@ int nint_set_strategy(nint_handle* h, int strategy) {
     if (rc == NINT_OK && strategy == NINT_LINEAR && !h->d_cells) {
         DeviceGuard guard(h->device);
         if (guard.ok) rc = build_cells(h);
+    }
+    {
+        DeviceGuard guard(h->device);
+        if (guard.ok) {
+            build_tile(h);
+            probe_threshold(h);
+        }
     }
     return rc;
 }
@@ -1051,6 +1263,11 @@ int nint_last_query_order(nint_handle* h) {
     NINT_CUDA(cudaDeviceSynchronize());
     NINT_CUDA(cudaMemcpy(&v, flag, sizeof v, cudaMemcpyDeviceToHost));
     return v;
+}
+
+int nint_last_incoherent_route(nint_handle* h) {
+    if (!h) return fail(NINT_E_INVALID_ARGUMENT, -1, "handle is NULL");
+    return h->last_route.load(std::memory_order_relaxed);
 }
 
 const char* nint_last_error_message(void) { return t_err_msg.c_str(); }

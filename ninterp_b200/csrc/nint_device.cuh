@@ -981,36 +981,6 @@ __global__ void __launch_bounds__(kBlock, slab_ctas(N, (int)sizeof(T))) slab_ker
     }
 }
 
-// Decides the query-order mode of a batch from 4096 pairs of consecutive points spread over it: coherent when at
-// least half of the pairs sit in the same or a neighbouring axis-0 cell.  One CTA; axes are read from global memory.
-template <class T>
-__global__ void __launch_bounds__(256) order_probe_kernel(const __grid_constant__ Params<T> P, int* __restrict__ mode_flag) {
-    __shared__ int s_near, s_valid;
-    if (threadIdx.x == 0) s_near = s_valid = 0;
-    __syncthreads();
-    const AxisRef<T> a0 = load_axis<T>(P, P.pack, 0);
-    const unsigned* guess0 = reinterpret_cast<const unsigned*>(P.pack + P.guess_off[0]);
-    const unsigned n = (unsigned)P.n;
-    int near = 0, valid = 0;
-    for (unsigned s = threadIdx.x; s < 4096u; s += blockDim.x) {
-        const unsigned i = (unsigned)(((unsigned long long)s * (unsigned long long)(n - 1u)) >> 12);
-        if (i + 1u >= n) continue;
-        const T x0 = __ldg(P.coords[0] + (size_t)i * P.coord_stride);
-        const T x1 = __ldg(P.coords[0] + (size_t)(i + 1u) * P.coord_stride);
-        int k0, k1;
-        const bool ok0 = guess_cell<T, false>(a0, guess0, x0, k0);
-        const bool ok1 = guess_cell<T, false>(a0, guess0, x1, k1);
-        if (ok0 && ok1) {
-            ++valid;
-            if (abs(k0 - k1) <= 1) ++near;
-        }
-    }
-    atomicAdd(&s_near, near);
-    atomicAdd(&s_valid, valid);
-    __syncthreads();
-    if (threadIdx.x == 0) *mode_flag = (2 * s_near >= s_valid) ? kModeCoherent : kModeRandom;
-}
-
 // 0-D InterpND (n/mod.rs:104-110): every point evaluates to the single stored value.
 template <class T>
 __global__ void __launch_bounds__(kBlock) constant_kernel(const T* __restrict__ values, T* __restrict__ out,
@@ -1060,8 +1030,6 @@ template <class T>
 cudaError_t launch_fixed(const Params<T>& P, const LaunchCfg& cfg);
 template <class T>
 cudaError_t launch_nd(const Params<T>& P, const LaunchCfg& cfg);
-template <class T>
-cudaError_t launch_order_probe(const Params<T>& P, int* mode_flag, void* stream);
 template <class T>
 cudaError_t launch_pack_cells(const Params<T>& P, int ndim, T* out, unsigned long long total, int sm_count, void* stream);
 template <class T>

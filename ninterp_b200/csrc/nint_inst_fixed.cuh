@@ -45,13 +45,6 @@ cudaError_t launch_fixed<NINT_T>(const Params<NINT_T>& P, const LaunchCfg& cfg) 
 }
 
 template <>
-cudaError_t launch_order_probe<NINT_T>(const Params<NINT_T>& P, int* mode_flag, void* stream) {
-    order_probe_kernel<NINT_T><<<1, 256, 0, (cudaStream_t)stream>>>(P, mode_flag);
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    return cudaGetLastError();
-}
-
-template <>
 cudaError_t launch_pack_cells<NINT_T>(const Params<NINT_T>& P, int ndim, NINT_T* out, unsigned long long total,
                                       int sm_count, void* stream) {
     if (total == 0) return cudaSuccess;

@@ -1,0 +1,437 @@
+// nint_tile.cuh — the binned route for incoherent queries on 3-D tables beyond L2 (Linear).
+//
+// A random cell of a table that does not fit L2 costs 4-5 DRAM sectors, and even with an L2-resident slab the
+// gathers are bound by L2 sector bandwidth.  This route takes the gathers out of the memory
+// system altogether: queries are bucketed by grid tile and every tile's value sub-block is staged once in shared
+// memory by TMA (cp.async.bulk.tensor, UTMALDG), where the 2^N corner loads are LDS.
+//
+//   tile_bin_kernel   one point per thread: front-end, cell guess + verification and the weights t_d exactly as the
+//                     single pass computes them (fast_weights == first half of fast_point); the point's record
+//                     {t_0, t_1, t_2, index, cell inside the tile} is appended to the list of its (superchunk, tile)
+//                     with one global atomic.  Points that need the general path are finished here.
+//   tile_eval_kernel  persistent CTAs walk the (superchunk, tile) lists superchunk-major: TMA brings the tile's
+//                     (B0+1) x (B1+1) x (B2+1) values into shared memory (double buffered, mbarrier), the records are
+//                     read coalesced, blended from shared memory with the reference's operation order
+//                     (three/strategies.rs:37-49) and the results scattered to out[index].  A superchunk is 2^23
+//                     consecutive points, so the scatter stays inside a 64 MB window of `out` that L2 merges into
+//                     full lines before it reaches DRAM.
+//
+// The arithmetic is the single pass's: t_d is computed once (bin) by the same inlined functions and the blend uses
+// the same expression tree, so results are bit-identical whichever route a batch takes.
+#pragma once
+#include <cuda.h>
+
+#include "nint_device.cuh"
+
+namespace nint {
+
+constexpr int kTileThreads = 1024;      // tile_eval_kernel: one CTA per SM (two tile buffers fill its shared memory)
+constexpr unsigned kCursorStride = 8;   // u32 slots between list cursors: 32 bytes, so neighbours hit different L2 slices
+constexpr int kTileRecBytes = 32;
+
+// Geometry of the binned route, shared by both kernels.
+struct TileGeom {
+    int sh[3];            // log2(cells per tile) along each axis
+    int nt[3];            // tiles per axis
+    int ntiles;
+    int box[3];           // staged elements per axis: cells per tile + 1 (innermost padded to a 16-byte multiple)
+    unsigned tile_bytes;  // bytes TMA delivers per tile (box volume x sizeof(T))
+    unsigned buf_bytes;   // tile_bytes rounded up to 128
+    unsigned cap;         // records per (superchunk, tile) list
+    unsigned sc_shift;    // log2(points per superchunk)
+    unsigned n_sc;        // superchunks in this launch
+    unsigned* cursor;     // [n_sc * ntiles] list lengths, kCursorStride apart
+    unsigned char* records;  // [n_sc * ntiles][cap] records of kTileRecBytes
+};
+
+// First half of fast_point() for Linear: cell guess, verification and weights of every axis.  Same functions, same
+// order, so a point is accepted here exactly when the single pass accepts it, with the same k and t.
+template <class T, int N, bool IS_ND, bool UNI, bool FIRST>
+__device__ __forceinline__ bool fast_weights(const Params<T>& P, const unsigned char* pack, const T (&p)[N], int (&k)[N],
+                                             T (&t)[N]) {
+    constexpr bool kCollapse = IS_ND || (N == 1);
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const unsigned* guess = UNI ? nullptr : reinterpret_cast<const unsigned*>(pack + P.guess_off[d]);
+        ok = guess_cell<T, UNI>(load_axis<T>(P, pack, d), guess, p[d], k[d]) && ok;
+    }
+    if (!ok) return false;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        T a, w, r;
+        ok = verify_cell_linear<T, kCollapse, FIRST>(load_axis<T>(P, pack, d), p[d], k[d], a, w, r) && ok;
+        t[d] = div_markstein<T>(a, w, r);
+    }
+    if (!UNI && !ok) {
+        ok = true;
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            T a, w, r;
+            ok = verify_linear_retry<T, kCollapse, FIRST, UNI>(load_axis<T>(P, pack, d), p[d], k[d], a, w, r) && ok;
+            t[d] = div_markstein<T>(a, w, r);
+        }
+    }
+    return ok;
+}
+
+// three/strategies.rs:37-49 (and two/, n/): reduce axis 0 first, v_l * (1 - t) + v_u * t, every op rounded separately.
+template <class T, int N>
+__device__ __forceinline__ T blend_cube(T (&cube)[1 << N], const T (&t)[N]) {
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        const int half = 1 << (N - 1 - d);
+        const T td = t[d];
+        const T sd = T(1) - td;
+#pragma unroll
+        for (int j = 0; j < half; ++j) cube[j] = cube[j] * sd + cube[half + j] * td;
+    }
+    return cube[0];
+}
+
+__device__ __forceinline__ void st_record(unsigned char* dst, double t0, double t1, double t2, unsigned idx, unsigned loc) {
+    const unsigned long long meta = (unsigned long long)idx | ((unsigned long long)loc << 32);
+    asm volatile("st.global.cs.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "l"(__double_as_longlong(t0)),
+                 "l"(__double_as_longlong(t1)), "l"(__double_as_longlong(t2)), "l"(meta)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_record(const unsigned char* src, double& t0, double& t1, double& t2, unsigned& idx,
+                                          unsigned& loc) {
+    long long a, b, c;
+    unsigned long long meta;
+    asm volatile("ld.global.cs.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(meta) : "l"(src));
+    t0 = __longlong_as_double(a);
+    t1 = __longlong_as_double(b);
+    t2 = __longlong_as_double(c);
+    idx = (unsigned)meta;
+    loc = (unsigned)(meta >> 32);
+}
+
+// f32 interpolators use the same 32-byte record (the weights widen exactly)
+__device__ __forceinline__ void st_record(unsigned char* dst, float t0, float t1, float t2, unsigned idx, unsigned loc) {
+    st_record(dst, (double)t0, (double)t1, (double)t2, idx, loc);
+}
+__device__ __forceinline__ void ld_record(const unsigned char* src, float& t0, float& t1, float& t2, unsigned& idx,
+                                          unsigned& loc) {
+    double a, b, c;
+    ld_record(src, a, b, c, idx, loc);
+    t0 = (float)a;
+    t1 = (float)b;
+    t2 = (float)c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bin: the point loop of interp_kernel with the gather replaced by an append to the point's list.
+// ---------------------------------------------------------------------------------------------
+template <class T, bool IS_ND, int PRE, bool UNI>
+__global__ void __launch_bounds__(kBlock, 4) tile_bin_kernel(const __grid_constant__ Params<T> P,
+                                                              const __grid_constant__ TileGeom G) {
+    constexpr int N = 3;
+    extern __shared__ __align__(16) unsigned char smem_pack[];
+    if (P.mode_flag != nullptr && *P.mode_flag != P.mode_want) return;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(P.pack);
+        uint4* dst = reinterpret_cast<uint4*>(smem_pack);
+        for (unsigned i = threadIdx.x; i < P.pack_bytes / 16u; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    const unsigned char* pack = smem_pack;
+    const unsigned long long pol = make_table_policy(P.l2_frac);
+    __shared__ unsigned long long s_info[4];  // n_error, n_panic, first_error, first_panic
+    if (threadIdx.x < 4) s_info[threadIdx.x] = (threadIdx.x < 2) ? 0ull : ~0ull;
+    __syncthreads();
+
+    const unsigned n = (unsigned)P.n;
+    const unsigned stride = gridDim.x * blockDim.x;
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    Point<T, N> q;
+    if (i < n) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) q.v[d] = ld_stream(P.coords[d] + (size_t)i * P.coord_stride);
+    }
+    auto process = [&](unsigned i, const Point<T, N>& q) {
+        T p[N];
+        bool oob = false;
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            p[d] = (PRE == kPreClamp) ? clamp_coord(q.v[d], P.g0[d], P.gl[d]) : q.v[d];
+            if (PRE == kPreWrap) oob = oob || !(P.g0[d] <= q.v[d] && q.v[d] <= P.gl[d]);
+        }
+        if (PRE == kPreWrap) {
+            if (oob) {
+                const Point<T, N> w = wrap_point<T, N>(P, q);
+#pragma unroll
+                for (int d = 0; d < N; ++d) p[d] = w.v[d];
+            }
+        }
+        int k[N];
+        T t[N];
+        if (fast_weights<T, N, IS_ND, UNI, PRE == kPreClamp>(P, pack, p, k, t)) {
+            const unsigned tile = (unsigned)(((k[0] >> G.sh[0]) * G.nt[1] + (k[1] >> G.sh[1])) * G.nt[2] + (k[2] >> G.sh[2]));
+            const unsigned loc = (unsigned)(k[0] & ((1 << G.sh[0]) - 1)) | ((unsigned)(k[1] & ((1 << G.sh[1]) - 1)) << 8) |
+                                 ((unsigned)(k[2] & ((1 << G.sh[2]) - 1)) << 16);
+            const unsigned list = (i >> G.sc_shift) * (unsigned)G.ntiles + tile;
+            const unsigned slot = atomicAdd(G.cursor + (size_t)list * kCursorStride, 1u);
+            if (slot < G.cap) {
+                st_record(G.records + ((size_t)list * G.cap + slot) * kTileRecBytes, t[0], t[1], t[2], i, loc);
+            } else {
+                // list full (queries far from uniform): finish the point here from the plain table
+                long long base = 0;
+                long long step[N];
+#pragma unroll
+                for (int d = 0; d < N; ++d) {
+                    base += (long long)k[d] * P.vstride[d];
+                    step[d] = P.vstride[d];
+                }
+                T cube[1 << N];
+                gather_rows<T, N>(P.values + base, step, pol, false, cube);
+                st_stream(P.out + i, blend_cube<T, N>(cube, t));
+            }
+            if (P.status) P.status[i] = (uint8_t)NINT_STATUS_OK;
+            return;
+        }
+        const Outcome<T> o = general_point<T, N, IS_ND, NINT_LINEAR>(P, pack, q);
+        T result = o.value;
+        if (o.status != NINT_STATUS_OK) {
+            result = quiet_nan<T>();
+            const int slot = (o.status == NINT_STATUS_PANIC) ? 1 : 0;
+            atomicAdd(&s_info[slot], 1ull);
+            atomicMin(&s_info[2 + slot], (unsigned long long)i + P.index_base);
+        }
+        st_stream(P.out + i, result);
+        if (P.status) P.status[i] = (uint8_t)o.status;
+    };
+    Point<T, N> q2;
+    while (i < n) {
+        const unsigned in = i + stride;
+        const bool more = in < n;
+        if (more) {
+#pragma unroll
+            for (int d = 0; d < N; ++d) q2.v[d] = ld_stream(P.coords[d] + (size_t)in * P.coord_stride);
+        }
+        process(i, q);
+        if (!more) break;
+        i = in;
+        q = q2;
+    }
+    if (P.info) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (s_info[0]) {
+                atomicAdd((unsigned long long*)&P.info->n_error, s_info[0]);
+                atomicMin((unsigned long long*)&P.info->first_error, s_info[2]);
+            }
+            if (s_info[1]) {
+                atomicAdd((unsigned long long*)&P.info->n_panic, s_info[1]);
+                atomicMin((unsigned long long*)&P.info->first_panic, s_info[3]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Evaluate: TMA-staged tiles, records blended from shared memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// One tile: box (box[2], box[1], box[0]) of the table at element coordinates (c0 innermost) -> shared memory.
+__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1,
+                                              int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <class T>
+struct TileEval {
+    T* out;
+    const int* mode_flag;
+    int mode_want;
+};
+
+template <class T>
+__global__ void __launch_bounds__(kTileThreads, 1) tile_eval_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                     const __grid_constant__ TileEval<T> E,
+                                                                     const __grid_constant__ TileGeom G) {
+    constexpr int N = 3;
+    constexpr int kUnroll = 4;
+    extern __shared__ __align__(128) unsigned char smem_tiles[];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    if (E.mode_flag != nullptr && *E.mode_flag != E.mode_want) return;
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const unsigned nitems = G.n_sc * (unsigned)G.ntiles;
+    // this CTA's items: blockIdx.x, + gridDim.x, ...: superchunk-major, so that at any time all CTAs scatter into
+    // the same window of `out`
+    auto next_item = [&](unsigned j) {
+        while (j < nitems && G.cursor[(size_t)j * kCursorStride] == 0u) j += gridDim.x;
+        return j;
+    };
+    auto issue = [&](unsigned item, unsigned b) {
+        const int tile = (int)(item % (unsigned)G.ntiles);
+        const int t2 = tile % G.nt[2];
+        const int t1 = (tile / G.nt[2]) % G.nt[1];
+        const int t0 = tile / (G.nt[2] * G.nt[1]);
+        mbar_expect_tx(&s_bar[b], G.tile_bytes);
+        tma_load_tile(smem_tiles + (size_t)b * G.buf_bytes, &tmap, &s_bar[b], t2 << G.sh[2], t1 << G.sh[1], t0 << G.sh[0]);
+    };
+    const int sy = G.box[2];
+    const int sx = G.box[1] * G.box[2];
+
+    unsigned cur = next_item(blockIdx.x);
+    unsigned b = 0;
+    unsigned parity[2] = {0u, 0u};
+    if (tid == 0 && cur < nitems) issue(cur, 0);
+    while (cur < nitems) {
+        const unsigned nxt = next_item(cur + gridDim.x);
+        __syncthreads();  // every thread is done with the other buffer (the previous item's tile)
+        if (tid == 0 && nxt < nitems) issue(nxt, b ^ 1u);
+        const unsigned count = min(G.cursor[(size_t)cur * kCursorStride], G.cap);
+        const unsigned char* recs = G.records + (size_t)cur * G.cap * kTileRecBytes;
+        // the tile was requested one item ago and has normally landed by now
+        mbar_wait(&s_bar[b], parity[b]);
+        parity[b] ^= 1u;
+        const T* tile = reinterpret_cast<const T*>(smem_tiles + (size_t)b * G.buf_bytes);
+        for (unsigned base = 0; base < count; base += kTileThreads * kUnroll) {
+            T t[kUnroll][N];
+            unsigned idx[kUnroll], loc[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const unsigned r = base + u * kTileThreads + tid;
+                if (r < count) ld_record(recs + (size_t)r * kTileRecBytes, t[u][0], t[u][1], t[u][2], idx[u], loc[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const unsigned r = base + u * kTileThreads + tid;
+                if (r < count) {
+                    const int off = (int)(loc[u] & 0xffu) * sx + (int)((loc[u] >> 8) & 0xffu) * sy + (int)(loc[u] >> 16);
+                    const T* c = tile + off;
+                    T cube[1 << N];
+                    cube[0] = c[0];
+                    cube[1] = c[1];
+                    cube[2] = c[sy];
+                    cube[3] = c[sy + 1];
+                    cube[4] = c[sx];
+                    cube[5] = c[sx + 1];
+                    cube[6] = c[sx + sy];
+                    cube[7] = c[sx + sy + 1];
+                    E.out[idx[u]] = blend_cube<T, N>(cube, t[u]);
+                }
+            }
+        }
+        cur = nxt;
+        b ^= 1u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Order probe: footprint of windows of consecutive queries.
+//
+// kProbeWindows windows of kProbeWindowPts consecutive points, spread over the batch, one CTA each.  A window's
+// footprint is the number of distinct coarse tiles (8 cells per axis) its points fall into; the batch is coherent
+// when the mean footprint is at most `max_distinct` -- the host derives that bound from the number of coarse tiles
+// of the gathered table that fit a share of L2, so cell-ordered, tile-ordered, Morton-ordered and axis-sorted
+// batches all take the single pass, and uniformly random ones do not.
+// ---------------------------------------------------------------------------------------------
+constexpr int kProbeWindows = 8;
+constexpr int kProbeWindowPts = 4096;
+constexpr int kProbeThreads = 1024;
+constexpr int kProbeBits = 1 << 16;
+
+struct ProbeSlot {  // one per in-flight batch call (ring in the handle)
+    int mode;
+    unsigned sum;
+    unsigned ticket;
+    unsigned pad;
+};
+
+template <class T>
+__global__ void __launch_bounds__(kProbeThreads) order_probe2_kernel(const __grid_constant__ Params<T> P, int ndim, int shift,
+                                                                      unsigned max_distinct_total, ProbeSlot* slot) {
+    __shared__ unsigned s_bits[kProbeBits / 32];
+    __shared__ unsigned s_count;
+    for (unsigned w = threadIdx.x; w < kProbeBits / 32; w += blockDim.x) s_bits[w] = 0u;
+    if (threadIdx.x == 0) s_count = 0u;
+    __syncthreads();
+    const unsigned n = (unsigned)P.n;
+    const unsigned span = n > (unsigned)kProbeWindowPts ? n - (unsigned)kProbeWindowPts : 0u;
+    const unsigned start = (gridDim.x > 1) ? (unsigned)(((unsigned long long)span * blockIdx.x) / (gridDim.x - 1)) : 0u;
+    unsigned long long total_tiles = 1;
+    for (int d = 0; d < ndim; ++d) total_tiles *= (unsigned long long)(((max(P.L[d], 2) - 2) >> shift) + 1);
+    for (unsigned j = threadIdx.x; j < (unsigned)kProbeWindowPts; j += blockDim.x) {
+        const unsigned i = start + j;
+        if (i >= n) break;
+        unsigned long long lin = 0;
+        for (int d = 0; d < ndim; ++d) {
+            const AxisRef<T> a = load_axis<T>(P, P.pack, d);
+            const unsigned* guess = reinterpret_cast<const unsigned*>(P.pack + P.guess_off[d]);
+            const T x = __ldg(P.coords[d] + (size_t)i * P.coord_stride);
+            int k = 0;
+            if (a.L >= 2) guess_cell<T, false>(a, guess, x, k);
+            lin = lin * (unsigned long long)(((max(a.L, 2) - 2) >> shift) + 1) + (unsigned long long)(k >> shift);
+        }
+        const unsigned bit = (total_tiles <= (unsigned long long)kProbeBits)
+                                 ? (unsigned)lin
+                                 : (unsigned)(((lin * 0x9E3779B97F4A7C15ull) >> 40) & (kProbeBits - 1));
+        atomicOr(&s_bits[bit >> 5], 1u << (bit & 31u));
+    }
+    __syncthreads();
+    unsigned c = 0;
+    for (unsigned w = threadIdx.x; w < kProbeBits / 32; w += blockDim.x) c += __popc(s_bits[w]);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31u) == 0u) atomicAdd(&s_count, c);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&slot->sum, s_count);
+        __threadfence();
+        const unsigned ticket = atomicAdd(&slot->ticket, 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            const unsigned sum = atomicAdd(&slot->sum, 0u);
+            slot->mode = (sum <= max_distinct_total) ? kModeCoherent : kModeRandom;
+            slot->sum = 0u;
+            slot->ticket = 0u;
+        }
+    }
+}
+
+// Launch interface (nint_tile_f64.cu).
+struct TileLaunch {
+    int is_nd, all_uniform, sm_count;
+    unsigned smem_bytes;  // axis pack staged by the bin kernel
+    void* stream;
+};
+template <class T>
+cudaError_t launch_tile_bin(const Params<T>& P, const TileGeom& G, const TileLaunch& cfg);
+template <class T>
+cudaError_t launch_tile_eval(const CUtensorMap& tmap, const TileEval<T>& E, const TileGeom& G, const TileLaunch& cfg);
+template <class T>
+cudaError_t launch_order_probe2(const Params<T>& P, int ndim, int shift, unsigned max_distinct_total, ProbeSlot* slot, void* stream);
+
+}  // namespace nint

@@ -1,0 +1,81 @@
+// nint_tile_inst.cuh — instantiates the binned route (nint_tile.cuh) and the order probe for NINT_T.
+#include <atomic>
+
+#include "nint_tile.cuh"
+
+namespace nint {
+
+extern std::atomic<unsigned long long> g_launch_count;
+
+namespace {
+
+template <class T, bool IS_ND, int PRE, bool UNI>
+cudaError_t launch_bin_variant(const Params<T>& P, const TileGeom& G, const TileLaunch& cfg) {
+    auto kern = tile_bin_kernel<T, IS_ND, PRE, UNI>;
+    const unsigned smem = cfg.smem_bytes;
+    if (smem > 40u * 1024u) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    static thread_local unsigned cached_smem = ~0u;
+    static thread_local int cached_bps = 0;
+    int bps = cached_bps;
+    if (cached_smem != smem || bps == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kBlock, smem);
+        if (e != cudaSuccess) return e;
+        if (bps < 1) bps = 1;
+        cached_bps = bps;
+        cached_smem = smem;
+    }
+    const unsigned long long want = (P.n + kBlock - 1) / kBlock;
+    const unsigned long long cap = (unsigned long long)cfg.sm_count * (unsigned long long)bps;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (grid == 0) return cudaSuccess;
+    kern<<<grid, kBlock, smem, (cudaStream_t)cfg.stream>>>(P, G);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+template <class T, bool IS_ND, int PRE>
+cudaError_t launch_bin_uni(const Params<T>& P, const TileGeom& G, const TileLaunch& cfg) {
+    return cfg.all_uniform ? launch_bin_variant<T, IS_ND, PRE, true>(P, G, cfg) : launch_bin_variant<T, IS_ND, PRE, false>(P, G, cfg);
+}
+template <class T, bool IS_ND>
+cudaError_t launch_bin_pre(const Params<T>& P, const TileGeom& G, const TileLaunch& cfg) {
+    if (P.extrap == NINT_EXTRAPOLATE_CLAMP) return launch_bin_uni<T, IS_ND, kPreClamp>(P, G, cfg);
+    if (P.extrap == NINT_EXTRAPOLATE_WRAP) return launch_bin_uni<T, IS_ND, kPreWrap>(P, G, cfg);
+    return launch_bin_uni<T, IS_ND, kPrePlain>(P, G, cfg);
+}
+
+}  // namespace
+
+template <>
+cudaError_t launch_tile_bin<NINT_T>(const Params<NINT_T>& P, const TileGeom& G, const TileLaunch& cfg) {
+    return cfg.is_nd ? launch_bin_pre<NINT_T, true>(P, G, cfg) : launch_bin_pre<NINT_T, false>(P, G, cfg);
+}
+
+template <>
+cudaError_t launch_tile_eval<NINT_T>(const CUtensorMap& tmap, const TileEval<NINT_T>& E, const TileGeom& G,
+                                     const TileLaunch& cfg) {
+    auto kern = tile_eval_kernel<NINT_T>;
+    const unsigned smem = 2u * G.buf_bytes;
+    static thread_local unsigned configured = 0;
+    if (configured < smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    kern<<<(unsigned)cfg.sm_count, kTileThreads, smem, (cudaStream_t)cfg.stream>>>(tmap, E, G);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+template <>
+cudaError_t launch_order_probe2<NINT_T>(const Params<NINT_T>& P, int ndim, int shift, unsigned max_distinct_total, ProbeSlot* slot,
+                                        void* stream) {
+    order_probe2_kernel<NINT_T><<<kProbeWindows, kProbeThreads, 0, (cudaStream_t)stream>>>(P, ndim, shift, max_distinct_total, slot);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+}  // namespace nint

@@ -64,7 +64,8 @@ def test_config3_interp3d_linear_256cubed():
         got, st, info = gpu_eval(g, cols)
         assert_same(got, st, want, st_want, "random order")
         assert info == expected_info(st_want) and (st == 0).all()
-        assert _lib.lib().nint_last_query_order(g._h) == 2  # incoherent: slab passes over the plain table
+        assert _lib.lib().nint_last_query_order(g._h) == 2  # incoherent ...
+        assert _lib.lib().nint_last_incoherent_route(g._h) == 2  # ... binned tiles staged by TMA
         # cell-sorted order must give the same values as the unsorted batch, through the single pass
         order = np.lexsort([np.searchsorted(axes[2], cols[2]), np.searchsorted(axes[1], cols[1]),
                             np.searchsorted(axes[0], cols[0])])

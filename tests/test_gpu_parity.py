@@ -273,6 +273,10 @@ def test_slab_passes_and_order_probe(monkeypatch):
                                             (FIXED, (64,), np.float64, "nonuniform", 5), (ND, (17, 5, 4, 3), np.float32, "nonuniform", 4),
                                             (ND, (20, 6, 5), np.float64, "uniform", 1)]:
         monkeypatch.setenv("NINT_SLABS", str(passes))
+        # the probe counts distinct cells (shift 0) per window of 4096 consecutive points: a random window touches
+        # nearly every cell of these small grids, a window sorted along axis 0 one or two axis-0 layers
+        monkeypatch.setenv("NINT_PROBE_SHIFT", "0")
+        monkeypatch.setenv("NINT_PROBE_MAX_DISTINCT", str(int(np.prod([l - 1 for l in lens])) // 3))
         axes = _axes(rng, lens, dtype, mode)
         values = rng.uniform(-1, 1, lens).astype(dtype)
         for extrap in (ERROR, CLAMP, ENABLE, FILL):
@@ -290,6 +294,7 @@ def test_slab_passes_and_order_probe(monkeypatch):
             assert_same(got, st, want, st_want, f"slab random {lens} {extrap}")
             assert info == expected_info(st_want)
             assert _lib.lib().nint_last_query_order(g._h) == 2
+            assert _lib.lib().nint_last_incoherent_route(g._h) == 1
             # coherent order: sorted along axis 0
             order = np.argsort(cols[0], kind="stable")
             cols_s = [c[order] for c in cols]
@@ -309,6 +314,73 @@ def test_slab_passes_and_order_probe(monkeypatch):
     assert _lib.lib().nint_last_query_order(g._h) == 0
 
 
+def test_binned_tile_route(monkeypatch):
+    # Incoherent batches on 3-D Linear tables beyond L2 are bucketed by grid tile and evaluated from TMA-staged tiles
+    # in shared memory (nint_tile.cuh).  Forced here on small tables, with small superchunks and segments so that a
+    # batch spans several of both, and with queries piled into one tile so that lists overflow.
+    from gpu_util import assert_same, expected_info, gpu_eval, make_pair
+
+    from ninterp_b200 import _lib
+
+    monkeypatch.setenv("NINT_SLAB_MIN_BYTES", "0")
+    monkeypatch.setenv("NINT_SLAB_MIN_POINTS", "0")
+    monkeypatch.setenv("NINT_ROUTE", "tile")
+    monkeypatch.setenv("NINT_PROBE_SHIFT", "0")
+    rng = np.random.default_rng(4242)
+    n = 300_001
+    for kind, lens, dtype, mode, sc_shift, seg_shift in [(FIXED, (40, 9, 8), np.float64, "uniform", 16, 17),
+                                                         (FIXED, (37, 35, 70), np.float64, "nonuniform", 15, 17),
+                                                         (ND, (21, 40, 36), np.float32, "nonuniform", 17, 28),
+                                                         (ND, (50, 18, 34), np.float64, "uniform", 23, 28),
+                                                         (FIXED, (18, 67, 72), np.float32, "uniform", 14, 16)]:
+        monkeypatch.setenv("NINT_TILE_SC_SHIFT", str(sc_shift))
+        monkeypatch.setenv("NINT_TILE_SEG_SHIFT", str(seg_shift))
+        # distinct cells per window of 4096 consecutive points: ~4000 (or every cell) in random order, the cells of a
+        # short run in cell order
+        monkeypatch.setenv("NINT_PROBE_MAX_DISTINCT", str(min(int(np.prod([l - 1 for l in lens])) // 3, 2000)))
+        axes = _axes(rng, lens, dtype, mode)
+        values = rng.uniform(-1, 1, lens).astype(dtype)
+        for extrap in (ERROR, CLAMP, ENABLE, FILL, WRAP):
+            g, o = make_pair(kind, axes, values, LIN, extrap, fill=-2.5, dtype=dtype)
+            cols = _queries(rng, axes, n, dtype, 0.05)
+            for d in range(3):  # nodes (tile boundaries are nodes), their neighbours, non-finite values
+                a = np.asarray(axes[d], dtype=dtype)
+                special = np.concatenate([a, np.nextafter(a, dtype(np.inf)), np.nextafter(a, dtype(-np.inf)),
+                                          np.array([np.nan, np.inf, -np.inf], dtype=dtype)])
+                where = rng.choice(n, special.size, replace=False)
+                cols[d][where] = special
+            want, st_want = o.eval(cols, nthreads=O.max_threads())
+            got, st, info = gpu_eval(g, cols)
+            assert_same(got, st, want, st_want, f"tiles random {lens} {extrap}")
+            assert info == expected_info(st_want)
+            assert _lib.lib().nint_last_query_order(g._h) == 2
+            assert _lib.lib().nint_last_incoherent_route(g._h) == 2
+            got, st, _ = gpu_eval(g, cols, aos=True)
+            assert_same(got, st, want, st_want, f"tiles aos {lens} {extrap}")
+            # coherent order (sorted by cell): the probe sends it to the single pass
+            order = np.lexsort([np.searchsorted(axes[2], cols[2]), np.searchsorted(axes[1], cols[1]),
+                                np.searchsorted(axes[0], cols[0])])
+            got, st, info = gpu_eval(g, [c[order] for c in cols])
+            assert_same(got, st, want[order], st_want[order], f"tiles sorted {lens} {extrap}")
+            assert _lib.lib().nint_last_query_order(g._h) == 1
+        # all queries in one corner of the grid, probe forced to "incoherent": the lists of that tile overflow and the
+        # bin kernel finishes the surplus itself
+        monkeypatch.setenv("NINT_PROBE_MAX_DISTINCT", "0")
+        g, o = make_pair(kind, axes, values, LIN, ERROR, dtype=dtype)
+        cols = [rng.uniform(a[0], a[min(3, len(a) - 1)], n).astype(dtype) for a in axes]
+        got, st, info = gpu_eval(g, cols)
+        want, st_want = o.eval(cols, nthreads=O.max_threads())
+        assert_same(got, st, want, st_want, f"tiles overflow {lens}")
+        assert _lib.lib().nint_last_incoherent_route(g._h) == 2
+    # a last axis whose byte length is not a multiple of 16 cannot be described to TMA: slab passes take over
+    monkeypatch.setenv("NINT_PROBE_MAX_DISTINCT", "0")
+    g, o = make_pair(FIXED, _axes(rng, (30, 8, 7), np.float64), rng.uniform(-1, 1, (30, 8, 7)), LIN, ERROR)
+    cols = _queries(rng, g.data.grid, 50_000, np.float64, 0.05)
+    got, st, _ = gpu_eval(g, cols)
+    assert_same(got, st, *o.eval(cols), "odd last axis")
+    assert _lib.lib().nint_last_incoherent_route(g._h) == 1
+
+
 def test_concurrent_batches_on_one_handle(monkeypatch):
     # include/ninterp_cuda.h: a handle is immutable during batch calls, so several host threads may evaluate
     # batches on their own streams at once -- on the single-pass route and on the probed one (order flag ring)
@@ -322,10 +394,17 @@ def test_concurrent_batches_on_one_handle(monkeypatch):
     monkeypatch.setenv("NINT_SLAB_MIN_POINTS", "0")
     rng = np.random.default_rng(2024)
     dev = torch.device("cuda", 0)
-    for passes in ("0", "3"):
-        monkeypatch.setenv("NINT_SLABS", passes)
-        axes = _axes(rng, (40, 9, 7), np.float64, "uniform")
-        values = rng.uniform(-1, 1, (40, 9, 7))
+    monkeypatch.setenv("NINT_PROBE_SHIFT", "0")
+    monkeypatch.setenv("NINT_PROBE_MAX_DISTINCT", "600")
+    for passes in ("0", "3", "tile"):
+        if passes == "tile":  # binned route: every call draws its lists from the handle's pool in stream order
+            monkeypatch.delenv("NINT_SLABS")
+            monkeypatch.setenv("NINT_ROUTE", "tile")
+            monkeypatch.setenv("NINT_TILE_SC_SHIFT", "16")
+        else:
+            monkeypatch.setenv("NINT_SLABS", passes)
+        axes = _axes(rng, (40, 9, 8), np.float64, "uniform")
+        values = rng.uniform(-1, 1, (40, 9, 8))
         g, o = make_pair(FIXED, axes, values, LIN, ERROR, dtype=np.float64)
         jobs = []
         for t in range(6):
