@@ -239,18 +239,24 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Waits for the phase with the given parity.  try_wait suspends the thread for a hardware-bounded time per attempt; the
+// attempt count is bounded too, so that a descriptor the hardware rejects ends in a trap rather than a hung GPU.
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    const unsigned addr = smem_u32(bar);
+    for (unsigned tries = 0; tries < (1u << 24); ++tries) {
+        unsigned done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
 }
 // One tile: box (box[2], box[1], box[0]) of the table at element coordinates (c0 innermost) -> shared memory.
 __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1,
