@@ -1,20 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — Interp3D Linear f64, 256^3 uniform grid, 1e9 query points per GPU (BASELINE.json configs[2]).
+"""bench.py — Interp3D Linear f64, 256^3 uniform grid, 1e9 uniformly random query points sharded over the GPUs
+(BASELINE.json configs[2]; SURVEY.md section 8d cfg 3).
 
-One step = one pass of the hot path (`Interpolator::interpolate` for every point of the batch) over the
-whole synthetic batch.  `value` is device-timed with the queries already resident in HBM; `e2e` is the
-same metric through the C ABI's host-buffer call (pinned host points in, host values out, copies inside
-the timed region).  `--impl reference` times the CPU restatement of the reference (the oracle; the
-Rust crate cannot be built in this image) on all host threads.
+One step = one pass of the hot path (`Interpolator::interpolate` for every point of the batch) over the whole
+synthetic batch.  `value` is device-timed with the queries already resident in HBM; `e2e` is the same metric
+through the C ABI's host-buffer call (pinned host points in, host values out, copies inside the timed region),
+with a plain-copy ceiling measured beside it.  `--impl reference` times the CPU restatement of the reference
+(the oracle; the Rust crate cannot be built in this image) on all host threads.
 
-Launch: `python bench.py --gpus 1`, or under torchrun with one rank per GPU (weak scaling: every rank
-evaluates its own `--points` queries against a replicated grid; there is no data-path collective).
+Launch: `python bench.py --gpus 1`, or under torchrun with one rank per GPU.  Strong scaling: the 1e9 points are
+split into contiguous ranges of n/G points (the loop being replaced is benches/benchmark.rs:149-151), the grid is
+replicated and there is no data-path collective.  `variants` carries the other BASELINE configurations and query
+orders, each with its own roofline fraction, clocks and parity sample.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -37,12 +42,13 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--points", type=float, default=1e9, help="query points per GPU per step")
-    ap.add_argument("--e2e-points", type=float, default=None, help="points per end-to-end step (default: --points, bounded by host RAM)")
-    ap.add_argument("--no-variants", action="store_true", help="skip the cell-sorted / non-uniform variants")
+    ap.add_argument("--points", type=float, default=1e9, help="query points per step, all GPUs together")
+    ap.add_argument("--e2e-points", type=float, default=None, help="points per end-to-end step per GPU (default: the rank's share, bounded by host RAM)")
+    ap.add_argument("--no-variants", action="store_true", help="skip the other query orders and BASELINE configurations")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--parity-seconds", type=float, default=40.0, help="CPU time budget of the whole-batch parity report")
     return ap.parse_args()
 
 
@@ -64,10 +70,10 @@ def config_dict(points, n_gpus, workload="interp3d_linear_f64_256cubed_uniform_g
         "workload": workload,
         "interpolator": "Interp3D", "strategy": "Linear", "extrapolate": "Error",
         "grid": [GRID, GRID, GRID], "grid_spacing": "uniform",
-        "points_per_gpu": int(points), "query_order": "uniform random (unsorted)",
+        "points_total": int(points), "points_per_gpu": int(points) // max(n_gpus, 1), "query_order": "uniform random (unsorted)",
         "query_layout": "struct of arrays, resident in HBM",
-        "l2_policy": "inputs (32 GB/step) exceed L2; no flush needed",
-        "sharding": f"queries sharded over {n_gpus} GPU(s), grid replicated, no collective",
+        "l2_policy": "inputs (32 GB/step over all GPUs) exceed L2; no flush needed",
+        "sharding": f"queries split into {n_gpus} contiguous range(s) of n/G points, grid replicated, no collective",
     }
 
 
@@ -160,7 +166,7 @@ def run_reference(args, rank):
     sample = f"{n} uniform random points per step of the 1e9-point workload, {threads} OpenMP threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args.points, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
@@ -189,46 +195,105 @@ def _cpu_model():
     return "unknown"
 
 
-# ------------------------------------------------------------------------------------- b200 arm
-def gen_random(torch, n, dev, seed, chunk=1 << 27):
+def _git_head():
+    try:
+        return subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT, capture_output=True, text=True).stdout.strip() or None
+    except Exception:
+        return None
+
+
+def kernel_source_sha():
+    """Hash of the CUDA sources: profiles/traffic.json records the one its ncu capture was taken with."""
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "ninterp_b200" / "csrc").glob("*.cu*")):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+# ------------------------------------------------------------------------------------- query generators (device)
+def gen_random(torch, n, dev, seed, chunk=1 << 27, ncols=3, dtype=None, lo=0.0, hi=1.0):
+    dtype = dtype or torch.float64
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
-    cols = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3)]
+    cols = [torch.empty(n, dtype=dtype, device=dev) for _ in range(ncols)]
     for c in cols:
         for s in range(0, n, chunk):
             e = min(n, s + chunk)
-            c[s:e] = torch.rand(e - s, dtype=torch.float64, device=dev, generator=gen)
+            c[s:e] = torch.rand(e - s, dtype=dtype, device=dev, generator=gen)
+            if lo != 0.0 or hi != 1.0:
+                c[s:e].mul_(hi - lo).add_(lo)
     return cols
 
 
-def fill_cell_sorted(torch, cols, dev, seed, chunk=1 << 26, GRID=GRID):
-    """Overwrites cols with queries visited in grid-cell order (what a pre-binned caller provides)."""
+def _fill_from_cells(torch, cols, dev, seed, cell_of, chunk=1 << 26, GRID=GRID):
+    """cols[d][i] = (cell_d(i) + U[0,1)) * h, where cell_of(i) -> (cx, cy, cz) int64 tensors for an index range."""
     n = cols[0].numel()
-    ncell = (GRID - 1) ** 3
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
     h = 1.0 / (GRID - 1)
     for s in range(0, n, chunk):
         e = min(n, s + chunk)
         i = torch.arange(s, e, dtype=torch.int64, device=dev)
-        cell = (i.to(torch.float64) * (ncell / n)).to(torch.int64).clamp_(max=ncell - 1)
-        cz = cell % (GRID - 1)
-        cy = (cell // (GRID - 1)) % (GRID - 1)
-        cx = cell // ((GRID - 1) * (GRID - 1))
-        for col, c in zip(cols, (cx, cy, cz)):
+        cells = cell_of(i, n)
+        for col, c in zip(cols, cells):
             u = torch.rand(e - s, dtype=torch.float64, device=dev, generator=gen)
-            col[s:e] = ((c.to(torch.float64) + u) * h).clamp_(0.0, 1.0)
-        del i, cell, cx, cy, cz
+            col[s:e] = ((c.clamp_(max=GRID - 2).to(torch.float64) + u) * h).clamp_(0.0, 1.0)
+        del i, cells
 
 
-def time_steps(torch, dist, interp, cols, out, steps, warmup, world, sampler=None):
+def fill_cell_sorted(torch, cols, dev, seed, GRID=GRID):
+    """Queries visited in grid-cell order, C order of the cells (what a caller that sorts by cell provides)."""
+    ncell = (GRID - 1) ** 3
+
+    def cell_of(i, n):
+        cell = (i.to(torch.float64) * (ncell / n)).to(torch.int64).clamp_(max=ncell - 1)
+        return cell // ((GRID - 1) * (GRID - 1)), (cell // (GRID - 1)) % (GRID - 1), cell % (GRID - 1)
+
+    _fill_from_cells(torch, cols, dev, seed, cell_of, GRID=GRID)
+
+
+def fill_tile_sorted(torch, cols, dev, seed, GRID=GRID, T=8):
+    """Queries grouped by tiles of T^3 cells (tiles in C order), uniformly random inside a tile: what a cheap
+    binning pass over coarse tiles emits."""
+    nt = (GRID - 1 + T - 1) // T
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed + 1)
+
+    def cell_of(i, n):
+        tile = (i.to(torch.float64) * (nt ** 3 / n)).to(torch.int64).clamp_(max=nt ** 3 - 1)
+        out = []
+        for t in (tile // (nt * nt), (tile // nt) % nt, tile % nt):
+            out.append(t * T + torch.randint(0, T, t.shape, dtype=torch.int64, device=dev, generator=gen))
+        return tuple(out)
+
+    _fill_from_cells(torch, cols, dev, seed, cell_of, GRID=GRID)
+
+
+def fill_morton(torch, cols, dev, seed, GRID=GRID):
+    """Queries visited along the Morton (Z-order) curve of the cells."""
+    bits = int(np.ceil(np.log2(GRID)))
+
+    def cell_of(i, n):
+        m = (i.to(torch.float64) * ((1 << (3 * bits)) / n)).to(torch.int64).clamp_(max=(1 << (3 * bits)) - 1)
+        cx, cy, cz = torch.zeros_like(m), torch.zeros_like(m), torch.zeros_like(m)
+        for b in range(bits):
+            cz |= ((m >> (3 * b)) & 1) << b
+            cy |= ((m >> (3 * b + 1)) & 1) << b
+            cx |= ((m >> (3 * b + 2)) & 1) << b
+        return cx, cy, cz
+
+    _fill_from_cells(torch, cols, dev, seed, cell_of, GRID=GRID)
+
+
+# ------------------------------------------------------------------------------------- timing
+def time_steps(torch, dist, interp, cols, out, steps, warmup, world, sampler=None, status=None):
     """W warm-up + K timed steps; returns (max-over-ranks seconds for K steps, per-step kernel ms list, clocks).
-    time_steps.launches = kernels this rank launched inside the timed region (a batch call is one launch, or an
-    order probe plus its passes on tables well beyond L2)."""
+    time_steps.launches = kernels this rank launched inside the timed region."""
     from ninterp_b200 import _lib
 
     for _ in range(warmup):
-        interp.interpolate_batch(cols, out=out)
+        interp.interpolate_batch(cols, out=out, status=status)
     torch.cuda.synchronize()
     launches0 = _lib.lib().nint_launch_count()
     if world > 1:
@@ -239,7 +304,7 @@ def time_steps(torch, dist, interp, cols, out, steps, warmup, world, sampler=Non
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     ev[0].record()
     for k in range(steps):
-        interp.interpolate_batch(cols, out=out)
+        interp.interpolate_batch(cols, out=out, status=status)
         ev[k + 1].record()
     torch.cuda.synchronize()
     time_steps.launches = _lib.lib().nint_launch_count() - launches0
@@ -277,12 +342,110 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+# ------------------------------------------------------------------------------------- parity
+class Checker:
+    """Compares device results with the CPU oracle (test infrastructure: the checker, never the thing measured)."""
+
+    def __init__(self):
+        sys.path.insert(0, str(ROOT / "tests"))
+        import oracle_binding as O
+
+        self.O = O
+        self.threads = host_threads(O)
+
+    def oracle(self, axes, values, strategy, extrap, fill=0.0, kind=0, dtype=np.float64):
+        return self.O.Oracle(axes, values, strategy, extrap, fill=fill, kind=kind, dtype=dtype)
+
+    @staticmethod
+    def mismatches(got, want):
+        u = np.uint64 if got.dtype == np.float64 else np.uint32
+        same = (got.view(u) == want.view(u)) | (np.isnan(got) & np.isnan(want))
+        return int(np.count_nonzero(~same))
+
+    def check_slices(self, torch, o, cols, out, status, slices):
+        """slices: list of (start, stop, step).  Returns a parity report over their union."""
+        checked = mism = st_mism = 0
+        t0 = time.perf_counter()
+        for (a, b, s) in slices:
+            sub = [c[a:b:s].contiguous().cpu().numpy() for c in cols]
+            got = out[a:b:s].contiguous().cpu().numpy()
+            want, st_want = o.eval(sub, nthreads=self.threads)
+            mism += self.mismatches(got, want)
+            if status is not None:
+                st_mism += int(np.count_nonzero(status[a:b:s].contiguous().cpu().numpy() != st_want))
+            else:
+                st_mism += int(np.count_nonzero(st_want))  # the timed workloads are all in range: every status is Ok
+            checked += len(got)
+        return {"points_checked": checked, "mismatches": mism, "status_mismatches": st_mism,
+                "seconds": round(time.perf_counter() - t0, 2)}
+
+
+def sample_slices(n, sample=64_000_000, tail=4_000_000):
+    """A strided sample across the whole batch plus its last points."""
+    step = max(1, n // sample)
+    sl = [(0, n, step)] if step > 1 else [(0, n, 1)]
+    if step > 1:
+        sl.append((max(0, n - tail), n, 1))
+    return sl
+
+
+def whole_batch_report(torch, ck, o, cols, out, seconds):
+    """Zero-mismatch report over the whole batch where the CPU keeps up (about 16 s per 1e9 points on 16 threads),
+    else over evenly spread blocks (always the first and the last) that fit the time budget."""
+    n = cols[0].numel()
+    block = 1 << 25
+    blocks = [(s, min(n, s + block), 1) for s in range(0, n, block)]
+    rep = ck.check_slices(torch, o, cols, out, None, blocks[:1])
+    per_block = max(rep["seconds"], 1e-3)
+    k = int(min(len(blocks) - 1, max(1, seconds / per_block - 1)))
+    rest = blocks[1:]
+    pick = sorted({int(round(j * (len(rest) - 1) / max(k - 1, 1))) for j in range(k)}) if rest else []
+    if rest and (len(rest) - 1) not in pick:
+        pick.append(len(rest) - 1)
+    rep2 = ck.check_slices(torch, o, cols, out, None, [rest[j] for j in pick]) if pick else {"points_checked": 0, "mismatches": 0, "status_mismatches": 0, "seconds": 0}
+    total = {k_: rep[k_] + rep2[k_] for k_ in ("points_checked", "mismatches", "status_mismatches")}
+    total["seconds"] = round(rep["seconds"] + rep2["seconds"], 2)
+    total["coverage"] = ("whole batch" if total["points_checked"] == n else
+                         f"{1 + len(pick)} of {len(blocks)} blocks of {block} points spread evenly over the batch, first and last included")
+    total["oracle_threads"] = ck.threads
+    return total
+
+
+def bits_checksum(torch, out):
+    """Order-independent checksum of the result bits (wrapping 64-bit sum)."""
+    v = out.view(torch.int64) if out.dtype == torch.float64 else out.view(torch.int32).to(torch.int64)
+    return int(v.sum().item()) & 0xFFFFFFFFFFFFFFFF
+
+
+def routes_checksum(torch, interp, cols, out, status=None):
+    """The same batch through every route the library has for it (binned tiles, slab passes, single pass):
+    the result bits must not depend on the route."""
+    sums = {}
+    saved = {k: os.environ.get(k) for k in ("NINT_ROUTE",)}
+    try:
+        for route in ("tile", "slab", "single"):
+            os.environ["NINT_ROUTE"] = route
+            out.zero_()
+            interp.interpolate_batch(cols, out=out, status=status)
+            torch.cuda.synchronize()
+            sums[route] = bits_checksum(torch, out)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return {"checksums": {k: f"{v:016x}" for k, v in sums.items()}, "identical": len(set(sums.values())) == 1}
+
+
+# ------------------------------------------------------------------------------------- b200 arm
 def run_b200(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
 
     import ninterp_b200 as nb
     from ninterp_b200 import _lib
+    from ninterp_b200.sharding import shard_range
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device: ninterp_b200 has no CPU fallback")
@@ -291,7 +454,9 @@ def run_b200(args, rank, local_rank, world):
     numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n = int(args.points)
+    n_total = int(args.points)
+    lo, hi = shard_range(n_total, rank, world)
+    n = hi - lo  # this rank's contiguous share (strong scaling)
     lib = _lib.lib()
 
     axes, values = grid_and_values()
@@ -299,87 +464,131 @@ def run_b200(args, rank, local_rank, world):
     cols = gen_random(torch, n, dev, seed=1234567890 + rank)
     out = torch.empty(n, dtype=torch.float64, device=dev)
 
-    sampler = ClockSampler(local_rank)
-    secs, per_step, clocks = time_steps(torch, dist, interp, cols, out, args.steps, args.warmup, world, sampler)
-    launches_rank = int(time_steps.launches)
-    launches = torch.tensor([launches_rank], dtype=torch.int64, device=dev)
-    order = int(lib.nint_last_query_order(interp._h))  # 0 no probe, 1 coherent, 2 incoherent (slab passes)
-    if world > 1:
-        dist.all_reduce(launches)
-    value = world * n * args.steps / secs / 1e9
-    kernel_ms = float(np.mean(per_step))
-
     peaks = {}
     try:
         peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    sampler = ClockSampler(local_rank)
+    secs, per_step, clocks = time_steps(torch, dist, interp, cols, out, args.steps, args.warmup, world, sampler)
+    launches_rank = int(time_steps.launches)
+    launches = torch.tensor([launches_rank], dtype=torch.int64, device=dev)
+    order = int(lib.nint_last_query_order(interp._h))  # 0 no probe, 1 coherent, 2 incoherent
+    route = int(lib.nint_last_incoherent_route(interp._h)) if order == 2 else 0  # 1 slab passes, 2 binned tiles
+    if world > 1:
+        dist.all_reduce(launches)
+    value = n_total * args.steps / secs / 1e9
+    kernel_ms = float(np.mean(per_step))
+
     achieved = n * BYTES_PER_POINT / (kernel_ms * 1e-3) / 1e9
     # One batch call is the unit of accounting: a single interp_kernel launch, or (incoherent queries on a table
-    # well beyond L2) the order probe plus the slab passes, whose summed time and summed DRAM traffic are reported.
+    # well beyond L2) the order probe plus bin + evaluate launches per segment (or the slab passes); their summed
+    # time and summed DRAM traffic are what is reported.
     per_call = launches_rank // max(args.steps, 1)
-    slab = order == 2
-    traffic = None
+    traffic, traffic_note = None, None
     try:
-        key = "interp3d_linear_f64_uniform_random_slab_bytes_per_call" if slab else "interp3d_linear_f64_uniform_random_bytes_per_launch"
-        traffic = json.load(open(ROOT / "profiles" / "traffic.json")).get(key)
+        tj = json.load(open(ROOT / "profiles" / "traffic.json"))
+        key = {2: "interp3d_linear_f64_uniform_random_tiles_bytes_per_call", 1: "interp3d_linear_f64_uniform_random_slab_bytes_per_call"}.get(
+            route, "interp3d_linear_f64_uniform_random_bytes_per_launch")
+        traffic = tj.get(key)
+        if traffic is not None and world > 1:
+            traffic = traffic * n / 1e9  # the capture is of a 1e9-point call; a rank's share scales with its points
+        traffic_note = {"source": "profiles/traffic.json (ncu capture, dram__bytes_read.sum + dram__bytes_write.sum)",
+                        "capture_commit": tj.get("commit"), "capture_kernel_source_sha": tj.get("kernel_source_sha"),
+                        "stale": tj.get("kernel_source_sha") != kernel_source_sha()}
     except Exception:
         pass
+    kernel_name = {2: f"order_probe2_kernel + {(per_call - 2) // 2} x (tile_bin_kernel<double,...> + tile_eval_kernel<double>) per batch call",
+                   1: f"order_probe2_kernel + {per_call - 2} x slab_kernel<double,3,...> per batch call"}.get(
+        route, "interp_kernel<double,3,fixed,Linear,smem,plain,uniform>")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "kernel": (f"{per_call - 2} x slab_kernel<double,3,fixed,plain,uniform> + order_probe_kernel per batch call"
-                           if slab else "interp_kernel<double,3,fixed,Linear,smem,plain,uniform>"),
-                "kernel_ms": kernel_ms, "launches_per_call": per_call,
+                "traffic": traffic, "traffic_note": traffic_note,
+                "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "kernel": kernel_name, "kernel_ms": kernel_ms, "launches_per_call": per_call,
                 "algorithmic_bytes_per_point": BYTES_PER_POINT, "points_per_call": n}
 
-    # parity sample of the main workload, kept for the cpu_baseline leg
-    sample_n = 0
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample_n = min(n, 64_000_000)
-        sample_cols = [c[:sample_n].cpu().numpy() for c in cols]
-        sample_out = out[:sample_n].cpu().numpy()
+    ck = Checker() if (rank == 0 and not args.no_cpu_baseline) else None
+    parity = None
+    if ck:
+        o3 = ck.oracle(axes, values, ck.O.LINEAR, ck.O.ERROR)
+        parity = whole_batch_report(torch, ck, o3, cols, out, args.parity_seconds if world == 1 else 6.0)
+        parity["routes"] = routes_checksum(torch, interp, cols, out)
+    cpu_sample = None
+    if ck and world == 1:
+        m = min(n, 32_000_000)
+        cpu_sample = ([c[:m].cpu().numpy() for c in cols], out[:m].cpu().numpy())
+
+    def frac(points, ms, bpp=BYTES_PER_POINT):
+        return points * bpp / (ms * 1e-3) / 1e9 / peak
 
     variants = {}
     if not args.no_variants:
-        # (ii) queries pre-sorted into grid cells
-        fill_cell_sorted(torch, cols, dev, seed=7 + rank)
-        s2, ps2, ck2 = time_steps(torch, dist, interp, cols, out, args.steps, args.warmup, world, ClockSampler(local_rank))
-        ms2 = float(np.mean(ps2))
-        variants["uniform_grid_cell_sorted_queries"] = {
-            "value": world * n * args.steps / s2 / 1e9, "unit": UNIT, "kernel_ms": ms2, "kernel_ms_min": float(np.min(ps2)),
-            "roofline_frac": n * BYTES_PER_POINT / (ms2 * 1e-3) / 1e9 / peak, "clocks": ck2}
-        # (iii) non-uniform axes, unsorted random queries
+        vsteps = max(5, min(args.steps, 10))
+
+        def timed(interp_v, cols_v, out_v, status=None, steps=vsteps, bpp=BYTES_PER_POINT, oracle=None, sample=64_000_000):
+            s, ps, ckk = time_steps(torch, dist, interp_v, cols_v, out_v, steps, args.warmup, world, ClockSampler(local_rank), status=status)
+            ms = float(np.mean(ps))
+            m = cols_v[0].numel()
+            r = {"value": world * m * steps / s / 1e9, "unit": UNIT, "kernel_ms": ms, "kernel_ms_min": float(np.min(ps)),
+                 "roofline_frac": frac(m, ms, bpp), "algorithmic_bytes_per_point": bpp, "points_per_gpu": m, "steps": steps,
+                 "clocks": ckk, "query_order_verdict": int(lib.nint_last_query_order(interp_v._h)),
+                 "incoherent_route": int(lib.nint_last_incoherent_route(interp_v._h))}
+            if ck and oracle is not None:
+                r["parity_report"] = ck.check_slices(torch, oracle, cols_v, out_v, status, sample_slices(m, sample, min(4_000_000, sample)))
+                r["parity_report"]["checksum"] = f"{bits_checksum(torch, out_v):016x}"
+            return r
+
+        o3 = ck.oracle(axes, values, ck.O.LINEAR, ck.O.ERROR) if ck else None
+        # cfg 3 +status: the same batch with the per-point status mask written (33 B/point)
+        status = torch.empty(n, dtype=torch.uint8, device=dev)
+        variants["random_queries_with_status_mask"] = timed(interp, cols, out, status=status, bpp=33, oracle=o3, sample=16_000_000)
+        del status
+        # cfg 3 forced onto the older routes, for the record
+        for name, route_env in (("random_queries_slab_passes", "slab"), ("random_queries_single_pass", "single")):
+            os.environ["NINT_ROUTE"] = route_env
+            variants[name] = timed(interp, cols, out, steps=5)
+            os.environ.pop("NINT_ROUTE", None)
+        # query orders a pre-binning caller provides
+        for name, fill, seed in (("uniform_grid_cell_sorted_queries", fill_cell_sorted, 7), ("tile_sorted_8cubed_queries", fill_tile_sorted, 11),
+                                 ("morton_queries", fill_morton, 13)):
+            fill(torch, cols, dev, seed=seed + rank)
+            variants[name] = timed(interp, cols, out, steps=args.steps if name.startswith("uniform_grid_cell") else vsteps,
+                                   oracle=o3, sample=16_000_000)
+        # non-uniform axes, unsorted random queries
         axes_nu, _ = grid_and_values(uniform=False)
         interp_nu = nb.Interp3D(*axes_nu, values, nb.strategy.Linear, nb.Extrapolate.Error, device=local_rank)
         del cols
         cols = gen_random(torch, n, dev, seed=1234567890 + rank)
-        s3, ps3, _ = time_steps(torch, dist, interp_nu, cols, out, args.steps, args.warmup, world)
-        ms3 = float(np.mean(ps3))
-        variants["nonuniform_grid_random_queries"] = {
-            "value": world * n * args.steps / s3 / 1e9, "unit": UNIT, "kernel_ms": ms3,
-            "roofline_frac": n * BYTES_PER_POINT / (ms3 * 1e-3) / 1e9 / peak}
+        variants["nonuniform_grid_random_queries"] = timed(
+            interp_nu, cols, out, oracle=ck.oracle(axes_nu, values, ck.O.LINEAR, ck.O.ERROR) if ck else None, sample=16_000_000)
         interp_nu.close()
+        if world > 1:
+            variants["note"] = "variants run on every rank's share; values are whole-job aggregates"
+        variants.update(other_configs(torch, dist, nb, ck, timed, dev, local_rank, rank, world))
 
     # end to end through the C ABI with host buffers
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(torch, dist, interp, cols, args, world, dev)
+        e2e = run_e2e(torch, dist, interp, cols, args, world, dev, rank, local_rank, axes, values)
 
     del cols, out
     torch.cuda.empty_cache()
 
     cpu_baseline = None
-    if sample_n:
-        cpu_baseline = run_cpu_baseline(axes, values, sample_cols, sample_out, args.cpu_seconds)
+    if cpu_sample:
+        cpu_baseline = run_cpu_baseline(axes, values, cpu_sample[0], cpu_sample[1], args.cpu_seconds)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": config_dict(n, world), "clocks": clocks, "e2e": e2e,
+            "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_dict(n_total, world), "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches.item()), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "variants": variants, "gpu": torch.cuda.get_device_name(local_rank), "library": lib.nint_version().decode(),
+            "parity_report": parity, "variants": variants, "gpu": torch.cuda.get_device_name(local_rank),
+            "library": lib.nint_version().decode(), "commit": _git_head(), "kernel_source_sha": kernel_source_sha(),
+            "numa_cpus_rank0": len(numa_cpus) if numa_cpus else None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -387,8 +596,76 @@ def run_b200(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def run_e2e(torch, dist, interp, cols, args, world, dev):
+def other_configs(torch, dist, nb, ck, timed, dev, local_rank, rank, world):
+    """BASELINE.json configs 1, 2 and 4 at their stated sizes (per GPU), device-resident inputs."""
+    v = {}
+    rng = np.random.default_rng(20261020)
+    O = ck.O if ck else None
+    # cfg 1: Interp1D Linear f64, 1,000-node non-uniform grid, Extrapolate::Error, 1e6 and 4e8 points (16 B/point)
+    g = np.concatenate([[0.0], np.cumsum(rng.uniform(0.5, 1.5, 999))])
+    vals = rng.uniform(0, 1, 1000)
+    it = nb.Interp1D(g, vals, nb.strategy.Linear, nb.Extrapolate.Error, device=local_rank)
+    o = ck.oracle([g], vals, O.LINEAR, O.ERROR) if ck else None
+    for npts, name in ((1_000_000, "cfg1_interp1d_linear_f64_1000_nodes_1e6_points"), (400_000_000, "cfg1_interp1d_linear_f64_1000_nodes_4e8_points")):
+        cols = gen_random(torch, npts, dev, seed=21 + rank, ncols=1, hi=float(g[-1]))
+        out = torch.empty(npts, dtype=torch.float64, device=dev)
+        v[name] = timed(it, cols, out, bpp=16, oracle=o, sample=2_000_000)  # the reference scans all nodes per point: small sample
+        del cols, out
+    it.close()
+    # cfg 2: Interp2D Linear + Nearest f64, 2048 x 2048, Clamp, 1e8 points, ~10 % out of range (24 B/point)
+    ax2 = [np.arange(2048.0)] * 2
+    v2 = rng.uniform(0, 1, (2048, 2048))
+    cols = gen_random(torch, 100_000_000, dev, seed=22 + rank, ncols=2, lo=-0.05 * 2047, hi=1.05 * 2047)
+    out = torch.empty(100_000_000, dtype=torch.float64, device=dev)
+    for strat, code, name in ((nb.strategy.Linear, 0, "cfg2_interp2d_linear_f64_2048sq_clamp_1e8_points"),
+                              (nb.strategy.Nearest, 1, "cfg2_interp2d_nearest_f64_2048sq_clamp_1e8_points")):
+        it = nb.Interp2D(*ax2, v2, strat, nb.Extrapolate.Clamp, device=local_rank)
+        v[name] = timed(it, cols, out, bpp=24, oracle=ck.oracle(ax2, v2, code, O.CLAMP) if ck else None, sample=16_000_000)
+        it.close()
+    del cols, out
+    # cfg 4: InterpND Linear f32 N=5, 32^5 non-uniform grid, 2e8 points over [-0.25, 1.25) of the span, Wrap and Fill (24 B/point)
+    ax5 = [np.cumsum(rng.uniform(0.5, 1.5, 32)).astype(np.float32) for _ in range(5)]
+    v5 = rng.uniform(0, 1, (32,) * 5).astype(np.float32)
+    cols = gen_random(torch, 200_000_000, dev, seed=24 + rank, ncols=5, dtype=torch.float32, lo=-0.25, hi=1.25)
+    for c, a in zip(cols, ax5):
+        c.mul_(float(a[-1] - a[0])).add_(float(a[0]))
+    out = torch.empty(200_000_000, dtype=torch.float32, device=dev)
+    for ext, code, fill, name in ((nb.Extrapolate.Wrap, 3, 0.0, "cfg4_interpnd_linear_f32_n5_32pow5_wrap_2e8_points"),
+                                  (nb.Extrapolate.Fill(-1.0), 1, -1.0, "cfg4_interpnd_linear_f32_n5_32pow5_fill_2e8_points")):
+        it = nb.InterpND(ax5, v5, nb.strategy.Linear, ext, dtype=np.float32, device=local_rank)
+        v[name] = timed(it, cols, out, bpp=24,
+                        oracle=ck.oracle(ax5, v5, O.LINEAR, code, fill=fill, kind=O.KIND_ND, dtype=np.float32) if ck else None, sample=2_000_000)
+        it.close()
+    del cols, out
+    torch.cuda.empty_cache()
+    return v
+
+
+def copy_ceiling(torch, pts, res, n, steps):
+    """The same bytes as one end-to-end step, as plain pinned copies (H2D of the points and D2H of the values on two
+    streams at once, no kernels): the ceiling the host pipeline can reach on this link."""
+    d_in = torch.empty((min(n, 1 << 26), 3), dtype=torch.float64, device="cuda")
+    d_out = torch.empty(min(n, 1 << 26), dtype=torch.float64, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    blk = d_in.shape[0]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for s in range(0, n, blk):
+            e = min(n, s + blk)
+            with torch.cuda.stream(s1):
+                d_in[: e - s].copy_(pts[s:e], non_blocking=True)
+            with torch.cuda.stream(s2):
+                res[s:e].copy_(d_out[: e - s], non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return dt / steps
+
+
+def run_e2e(torch, dist, interp, cols, args, world, dev, rank, local_rank, axes, values):
     import psutil
+
+    import ninterp_b200 as nb
 
     n_dev = cols[0].numel()
     want = int(args.e2e_points) if args.e2e_points else n_dev
@@ -415,15 +692,46 @@ def run_e2e(torch, dist, interp, cols, args, world, dev):
         interp.interpolate_batch_host(pts_np, out=res_np)  # returns when res_np is complete on the host
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
     checksum = float(res_np[:: max(1, n // 1000)].sum())
-    out = {"value": world * n * steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": n * 24 * world,
+    # the plain-copy ceiling, all ranks at once like the leg above
+    if world > 1:
+        dist.barrier()
+    ceil_s = copy_ceiling(torch, pts, res, n, steps=max(2, steps // 2))
+    if world > 1:
+        t = torch.tensor([dt, ceil_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, ceil_s = float(t[0].item()), float(t[1].item())
+    value = world * n * steps / dt / 1e9
+    ceiling = world * n / ceil_s / 1e9
+    out = {"value": value, "unit": UNIT, "h2d_bytes_per_step": n * 24 * world,
            "host_cpus_rank0": len(os.sched_getaffinity(0)),
            "d2h_bytes_per_step": n * 8 * world, "points_per_step_per_gpu": n, "steps": steps, "ms_per_step": dt / steps * 1e3,
-           "api": "nint_interpolate_batch_host (AoS points in pinned host memory -> host values)", "checksum": checksum}
+           "api": "nint_interpolate_batch_host (AoS points in pinned host memory -> host values)", "checksum": checksum,
+           "copy_ceiling": {"value": ceiling, "unit": UNIT, "h2d_gb_s": world * n * 24 / ceil_s / 1e9, "d2h_gb_s": world * n * 8 / ceil_s / 1e9,
+                            "what": "the step's bytes as concurrent pinned cudaMemcpyAsync H2D + D2H on every rank, no kernels"},
+           "frac_of_copy_ceiling": value / ceiling}
+    # one process, all GPUs: nint_interpolate_batch_host_multi from rank 0 while the other ranks wait
+    if world > 1:
+        dist.barrier()
+        multi = None
+        if rank == 0:
+            try:
+                from ninterp_b200.multi import ReplicatedInterpolator
+
+                rep = ReplicatedInterpolator(lambda d: nb.Interp3D(*axes, values, nb.strategy.Linear, nb.Extrapolate.Error, device=d), range(world))
+                rep.interpolate_batch_host(pts_np, out=res_np)
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    rep.interpolate_batch_host(pts_np, out=res_np)
+                dtm = time.perf_counter() - t0
+                multi = {"value": n * steps / dtm / 1e9, "unit": UNIT, "points_per_step": n, "gpus": world,
+                         "api": "nint_interpolate_batch_host_multi (one process, one handle and one host thread per GPU)",
+                         "checksum": float(res_np[:: max(1, n // 1000)].sum())}
+                rep.close()
+            except Exception as ex:  # the leg is informational
+                multi = {"error": repr(ex)}
+        dist.barrier()
+        out["e2e_multi"] = multi
     del pts, res
     return out
 

@@ -523,6 +523,8 @@ int slab_windows(const nint_handle* h, size_t n) {
     const long long min_bytes = e_bytes ? std::atoll(e_bytes) : 256ll << 20;
     const long long min_points = e_points ? std::atoll(e_points) : 1ll << 22;
     const int forced = e_on ? std::atoi(e_on) : -1;
+    if (const char* route = std::getenv("NINT_ROUTE"))
+        if (!std::strcmp(route, "single")) return 0;
     if (forced == 0 || h->constant || h->strategy != NINT_LINEAR || h->extrap == NINT_EXTRAPOLATE_WRAP || !h->smem_axes) return 0;
     if (!(h->ax[0].flags & nint::kAxisFast) || (long long)n < min_points) return 0;
     const int cells0 = (int)h->axis_len[0] - 1;

@@ -20,3 +20,5 @@ echo "== f32 tile"; timeout 300 python tools/prof_case.py --case random --dtype 
 echo "== f32 slab"; NINT_ROUTE=slab timeout 300 python tools/prof_case.py --case random --dtype f32 --points 1e9 --launches 4
 } > gpurun_out/r2a_times.log 2>&1
 tail -5 gpurun_out/r2a_pytest.log; cat gpurun_out/r2a_times.log | grep -v "^+"
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/r2a_bench.json 2> gpurun_out/r2a_bench.err
+echo "bench rc=$?"; tail -c 1500 gpurun_out/r2a_bench.err
