@@ -51,6 +51,13 @@ int cuda_fail(cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
 
+// inside nint_interpolate_batch_host's chunk loop: drain the pipeline's streams before reporting the failure
+#define NINT_CUDA_DRAIN(call)                                                    \
+    do {                                                                         \
+        cudaError_t e__ = (call);                                                \
+        if (e__ != cudaSuccess) return drain_pipeline(h, cuda_fail(e__, #call)); \
+    } while (0)
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = false;
@@ -189,7 +196,7 @@ int validate_data(const nint_handle* h) {
 }
 
 // ------------------------------------------------------------------------------- axis pack
-unsigned align_up(unsigned v, unsigned a) { return (v + a - 1) / a * a; }
+unsigned long long align_up(unsigned long long v, unsigned long long a) { return (v + a - 1) / a * a; }
 
 // Bucket table of one axis.  Bucket b of width w_eff covers [g0 + b*w_eff, g0 + (b+1)*w_eff); a point
 // that the device maps to bucket b lies, with rounding, inside buckets b-1..b+1, so its node count
@@ -255,7 +262,10 @@ void classify_axis(const nint_handle* h, int d, AxisMeta& a) {
     }
     a.flags = strict ? nint::kAxisFast : 0;
     a.inv_h = 0.0;
-    const double span = a.gl - a.g0;
+    // the device forms p - g0 in T: an f32 axis whose span overflows f32 (e.g. -3e38 .. 3e38) has no usable
+    // bucket or cell formula even though the span is finite in double
+    const double span = (h->dtype == NINT_F32) ? (double)((float)a.gl - (float)a.g0) : a.gl - a.g0;
+    if (!std::isfinite(span)) a.flags = 0;  // general path only (full binary search, IEEE division)
     if (strict && std::isfinite(span) && span > 0.0) {
         const double hh = span / (double)(L - 1);
         bool uniform = true;
@@ -278,7 +288,7 @@ double make_buckets(const nint_handle* h, int d, double per_cell, AxisMeta& a, s
     const int L = a.L;
     int M = (int)std::min<double>(std::max(1.0, per_cell * (double)L), h->dtype == NINT_F64 ? 16777216.0 : 1048576.0);
     double inv_w = 0.0;
-    const double span = a.gl - a.g0;
+    const double span = (h->dtype == NINT_F32) ? (double)((float)a.gl - (float)a.g0) : a.gl - a.g0;  // as the device computes it
     if (L >= 2 && M >= 2 && std::isfinite(span) && span > 0.0) {
         inv_w = (double)M / span;
         if (h->dtype == NINT_F32) inv_w = (double)(float)inv_w;  // the device multiplies by this in T
@@ -298,8 +308,12 @@ int build_pack(nint_handle* h) {
     unsigned long long rec_bytes = 0;
     for (int d = 0; d < n; ++d) {
         classify_axis(h, d, h->ax[d]);
-        rec_bytes += align_up((unsigned)((h->axis_len[d] + 2) * 2 * es), 16);
+        rec_bytes += align_up((unsigned long long)(h->axis_len[d] + 2) * 2 * es, 16);
     }
+    // Offsets into the pack are 32-bit on the device (Params::node_off, guess_off, lut_off): records plus at most
+    // 16 Mi buckets of 12 bytes per axis must stay below 2 GiB
+    if (rec_bytes + (unsigned long long)n * (12ull << 24) >= (1ull << 31))
+        return fail(NINT_E_UNSUPPORTED, -1, "axes too long: the axis pack (%llu bytes of node records) exceeds 2 GiB", rec_bytes);
     unsigned long long smem_limit = kSmemLimit;
     if (const char* env = std::getenv("NINT_SMEM_LIMIT")) smem_limit = std::strtoull(env, nullptr, 10);
     // Bucket tables.  Every axis gets the {lo, hi} table the general path searches in (global memory only, 8 bytes
@@ -329,7 +343,7 @@ int build_pack(nint_handle* h) {
                 per_cell *= 2.0;
                 wide = make_buckets(h, d, per_cell, a, luts[d], guesses[d]);
             }
-            if (!uniform) guess_bytes += align_up((unsigned)(a.M * 4), 16);
+            if (!uniform) guess_bytes += align_up((unsigned long long)a.M * 4, 16);
         }
         return refined;
     };
@@ -343,7 +357,7 @@ int build_pack(nint_handle* h) {
         // records {node, cell reciprocal}; two {+inf, 0} pads (the bracket may look one and two nodes past
         // its upper bound).  Reciprocals only for cells whose width is comfortably normal (div_markstein).
         a.node_off = (unsigned)pack.size();
-        pack.resize(pack.size() + align_up((unsigned)((L + 2) * 2 * es), 16), 0);
+        pack.resize(pack.size() + (size_t)align_up((unsigned long long)(L + 2) * 2 * es, 16), 0);
         for (int l = 0; l < L + 2; ++l) {
             unsigned char* rec = pack.data() + a.node_off + (size_t)l * 2 * es;
             if (h->dtype == NINT_F64) {
@@ -373,14 +387,14 @@ int build_pack(nint_handle* h) {
         AxisMeta& a = h->ax[d];
         a.guess_off = (unsigned)pack.size();
         if (a.flags & nint::kAxisUniform) continue;
-        pack.resize(pack.size() + align_up((unsigned)(a.M * 4), 16), 0);
+        pack.resize(pack.size() + (size_t)align_up((unsigned long long)a.M * 4, 16), 0);
         std::memcpy(pack.data() + a.guess_off, guesses[d].data(), (size_t)a.M * 4);
     }
     h->pack_hot_bytes = (unsigned)pack.size();
     for (int d = 0; d < n; ++d) {  // {lo, hi} tables: read from global memory by the general path
         AxisMeta& a = h->ax[d];
         a.lut_off = (unsigned)pack.size();
-        pack.resize(pack.size() + align_up((unsigned)(a.M * 8), 16), 0);
+        pack.resize(pack.size() + (size_t)align_up((unsigned long long)a.M * 8, 16), 0);
         std::memcpy(pack.data() + a.lut_off, luts[d].data(), (size_t)a.M * 8);
     }
     h->pack_bytes = (unsigned)pack.size();
@@ -846,6 +860,34 @@ int ensure_pipeline(nint_handle* h) {
     return NINT_OK;
 }
 
+void free_pipeline(nint_handle* h);
+
+// ensure_pipeline() with its partial allocations released on failure
+int ensure_pipeline_or_free(nint_handle* h) {
+    const int rc = ensure_pipeline(h);
+    if (rc != NINT_OK) {
+        const std::string msg = t_err_msg;
+        free_pipeline(h);
+        cudaGetLastError();
+        t_err_msg = msg;
+    }
+    return rc;
+}
+
+// Error exit of the host pipeline: earlier chunks' copies may still be writing into the caller's buffers, so
+// nothing returns before the three streams have drained.
+int drain_pipeline(nint_handle* h, int rc) {
+    const std::string msg = t_err_msg;
+    const int dim = t_err_dim;
+    cudaStreamSynchronize(h->pipe.s_in);
+    cudaStreamSynchronize(h->pipe.s_k);
+    cudaStreamSynchronize(h->pipe.s_out);
+    cudaGetLastError();
+    t_err_msg = msg;
+    t_err_dim = dim;
+    return rc;
+}
+
 void free_pipeline(nint_handle* h) {
     Pipeline& p = h->pipe;
     for (Slot& s : p.slot) {
@@ -1015,8 +1057,8 @@ int nint_set_extrapolate(nint_handle* h, int extrapolate, const void* fill) {
     if (extrapolate < NINT_EXTRAPOLATE_ENABLE || extrapolate > NINT_EXTRAPOLATE_ERROR)
         return fail(NINT_E_INVALID_ARGUMENT, -1, "unknown extrapolate %d", extrapolate);
     if (extrapolate == NINT_EXTRAPOLATE_FILL && !fill) return fail(NINT_E_INVALID_ARGUMENT, -1, "Fill needs a value");
-    if (h->constant) return NINT_OK;  // zero/mod.rs:60-63 and 0-D InterpND: nothing to check against
-    int rc = check_extrapolate(h, h->extrap, extrapolate);  // three/mod.rs:240-244
+    std::lock_guard<std::mutex> lock(h->mu);  // not against batch calls in flight (those need external synchronisation, like &mut self)
+    int rc = check_extrapolate(h, h->extrap, extrapolate);  // three/mod.rs:240-244, n/mod.rs:342-346 (0-D InterpND included)
     if (rc != NINT_OK) return rc;
     h->extrap = extrapolate;
     if (extrapolate == NINT_EXTRAPOLATE_FILL) h->fill = load_elem(h->dtype, fill, 0);
@@ -1030,6 +1072,7 @@ int nint_set_strategy(nint_handle* h, int strategy) {
     if ((strategy == NINT_LEFT_NEAREST || strategy == NINT_RIGHT_NEAREST) &&
         !(h->kind == NINT_KIND_FIXED && h->ngrid == 1))
         return fail(NINT_E_UNSUPPORTED, -1, "LeftNearest/RightNearest exist for Interp1D only");
+    std::lock_guard<std::mutex> lock(h->mu);
     // three/mod.rs:259-271: the strategy is replaced first, then checked (and stays replaced on error)
     h->strategy = strategy;
     int rc = check_extrapolate(h, h->extrap, h->extrap);
@@ -1098,7 +1141,7 @@ int nint_interpolate_batch_host(nint_handle* h, int layout, const void* data, si
     std::lock_guard<std::mutex> lock(h->mu);
     DeviceGuard guard(h->device);
     if (!guard.ok) return fail(NINT_E_CUDA, -1, "cannot select CUDA device %d", h->device);
-    int rc = ensure_pipeline(h);
+    int rc = ensure_pipeline_or_free(h);
     if (rc != NINT_OK) return rc;
     Pipeline& p = h->pipe;
     rc = reset_info(h->d_info, p.s_k);
@@ -1111,38 +1154,38 @@ int nint_interpolate_batch_host(nint_handle* h, int layout, const void* data, si
         // the slot's input buffer is free once its previous kernel has run, its output buffers once
         // their previous copy-out has finished
         if (j >= (size_t)Pipeline::kSlots) {
-            NINT_CUDA(cudaStreamWaitEvent(p.s_in, s.k_done, 0));
-            NINT_CUDA(cudaStreamWaitEvent(p.s_k, s.out_done, 0));
+            NINT_CUDA_DRAIN(cudaStreamWaitEvent(p.s_in, s.k_done, 0));
+            NINT_CUDA_DRAIN(cudaStreamWaitEvent(p.s_k, s.out_done, 0));
         }
         const void* cols_dev[NINT_MAX_NDIM] = {};
         long long stride = 1;
         if (layout == NINT_LAYOUT_AOS) {
-            NINT_CUDA(cudaMemcpyAsync(s.d_in, (const unsigned char*)data + start * (size_t)nd * es, m * (size_t)nd * es,
+            NINT_CUDA_DRAIN(cudaMemcpyAsync(s.d_in, (const unsigned char*)data + start * (size_t)nd * es, m * (size_t)nd * es,
                                       cudaMemcpyHostToDevice, p.s_in));
             split_cols(h, s.d_in, &stride, cols_dev);
         } else {
             for (int d = 0; d < nd; ++d) {
                 unsigned char* dst = (unsigned char*)s.d_in + (size_t)d * p.chunk * es;
-                NINT_CUDA(cudaMemcpyAsync(dst, (const unsigned char*)cols_host[d] + start * es, m * es,
+                NINT_CUDA_DRAIN(cudaMemcpyAsync(dst, (const unsigned char*)cols_host[d] + start * es, m * es,
                                           cudaMemcpyHostToDevice, p.s_in));
                 cols_dev[d] = dst;
             }
         }
-        NINT_CUDA(cudaEventRecord(s.in_done, p.s_in));
-        NINT_CUDA(cudaStreamWaitEvent(p.s_k, s.in_done, 0));
+        NINT_CUDA_DRAIN(cudaEventRecord(s.in_done, p.s_in));
+        NINT_CUDA_DRAIN(cudaStreamWaitEvent(p.s_k, s.in_done, 0));
         rc = launch(h, cols_dev, stride, m, s.d_out, status_host ? s.d_status : nullptr, h->d_info, start, p.s_k);
-        if (rc != NINT_OK) return rc;
-        NINT_CUDA(cudaEventRecord(s.k_done, p.s_k));
-        NINT_CUDA(cudaStreamWaitEvent(p.s_out, s.k_done, 0));
-        NINT_CUDA(cudaMemcpyAsync((unsigned char*)out_host + start * es, s.d_out, m * es, cudaMemcpyDeviceToHost, p.s_out));
+        if (rc != NINT_OK) return drain_pipeline(h, rc);
+        NINT_CUDA_DRAIN(cudaEventRecord(s.k_done, p.s_k));
+        NINT_CUDA_DRAIN(cudaStreamWaitEvent(p.s_out, s.k_done, 0));
+        NINT_CUDA_DRAIN(cudaMemcpyAsync((unsigned char*)out_host + start * es, s.d_out, m * es, cudaMemcpyDeviceToHost, p.s_out));
         if (status_host)
-            NINT_CUDA(cudaMemcpyAsync(status_host + start, s.d_status, m, cudaMemcpyDeviceToHost, p.s_out));
-        NINT_CUDA(cudaEventRecord(s.out_done, p.s_out));
+            NINT_CUDA_DRAIN(cudaMemcpyAsync(status_host + start, s.d_status, m, cudaMemcpyDeviceToHost, p.s_out));
+        NINT_CUDA_DRAIN(cudaEventRecord(s.out_done, p.s_out));
     }
     nint_batch_info info;
-    NINT_CUDA(cudaStreamSynchronize(p.s_out));
-    NINT_CUDA(cudaMemcpyAsync(&info, h->d_info, sizeof info, cudaMemcpyDeviceToHost, p.s_k));
-    NINT_CUDA(cudaStreamSynchronize(p.s_k));
+    NINT_CUDA_DRAIN(cudaStreamSynchronize(p.s_out));
+    NINT_CUDA_DRAIN(cudaMemcpyAsync(&info, h->d_info, sizeof info, cudaMemcpyDeviceToHost, p.s_k));
+    NINT_CUDA_DRAIN(cudaStreamSynchronize(p.s_k));
     if (info_host) *info_host = info;
     if (info.n_panic)
         return fail(NINT_E_PANIC, -1, "the reference implementation would panic on %llu point(s), first at index %llu",

@@ -125,8 +125,12 @@ class _InterpBase:
 
     def set_strategy(self, strategy) -> None:
         """`InterpXD::set_strategy` for the strategy enums (three/mod.rs:259-271)."""
-        self.strategy = strategy  # the reference assigns before checking
-        check(L.lib().nint_set_strategy(self._h, strategy.code))
+        rc = L.lib().nint_set_strategy(self._h, strategy.code)
+        # the reference assigns before checking (three/mod.rs:259-271), so the new strategy stays in place when the
+        # check fails; a strategy the handle never took (not built in for this interpolator) leaves both unchanged
+        if rc not in (L.E_UNSUPPORTED, L.E_INVALID_ARGUMENT):
+            self.strategy = strategy
+        check(rc)
 
     def last_query_order(self) -> int:
         """Diagnostics: route of the most recent batch (0 no order probe ran, 1 coherent: single pass on the
@@ -172,6 +176,14 @@ class _InterpBase:
         dev = torch.device("cuda", self.device)
         if out is None:
             out = torch.empty(n, dtype=tdt, device=dev)
+        # caller-supplied result buffers are handed to the C ABI as raw pointers: check them here
+        for name, t, want_dt, want_n in (("out", out, (tdt,), n), ("status", status, (torch.uint8,), n),
+                                         ("info", info, (torch.int64, torch.uint64), 4)):
+            if t is None:
+                continue
+            if (not isinstance(t, torch.Tensor) or not t.is_cuda or t.device.index != self.device or t.dtype not in want_dt
+                    or not t.is_contiguous() or t.numel() < want_n):
+                raise EngineError(f"`{name}` must be a contiguous {want_dt[0]} tensor of at least {want_n} elements on cuda:{self.device}")
         if stream is None:
             stream = torch.cuda.current_stream(dev).cuda_stream
         st_ptr = C.c_void_p(status.data_ptr()) if status is not None else None
@@ -221,6 +233,7 @@ class _InterpBase:
             data = C.cast(arr, C.c_void_p)
         if out is None:
             out = np.empty(n, dtype=self.dtype)
+        _check_host_out(out, self.dtype, n)
         status = np.empty(n, dtype=np.uint8) if return_status else None
         info = L.BatchInfo()
         rc = lib.nint_interpolate_batch_host(self._h, layout, data, n, C.c_void_p(out.ctypes.data),
@@ -233,6 +246,13 @@ class _InterpBase:
             return out, status, dict(n_error=info.n_error, n_panic=info.n_panic, first_error=info.first_error,
                                      first_panic=info.first_panic)
         return out
+
+
+def _check_host_out(out, dtype, n):
+    """A caller-supplied host result buffer is written through a raw pointer: dtype, layout and length must fit."""
+    if (not isinstance(out, np.ndarray) or out.dtype != np.dtype(dtype) or not out.flags.c_contiguous
+            or not out.flags.writeable or out.size < n):
+        raise EngineError(f"`out` must be a writeable C-contiguous {np.dtype(dtype)} array of at least {n} elements")
 
 
 class Interp1D(_InterpBase):

@@ -12,6 +12,7 @@ import numpy as np
 
 from . import _lib as L
 from .error import InterpolateError, check
+from .interpolator import _check_host_out
 
 
 class ReplicatedInterpolator:
@@ -38,6 +39,7 @@ class ReplicatedInterpolator:
         n = pts.shape[0]
         if out is None:
             out = np.empty(n, dtype=self.dtype)
+        _check_host_out(out, self.dtype, n)
         status = np.empty(n, dtype=np.uint8) if return_status else None
         info = L.BatchInfo()
         hs = (C.c_void_p * len(self.replicas))(*[r._h for r in self.replicas])
