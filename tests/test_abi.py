@@ -57,6 +57,57 @@ def test_rust_sys_crate_declares_the_same_abi():
     assert wrapper.endswith(quoted) and len(quoted) > 2000
 
 
+def _split_args(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "([{<":
+            depth += 1
+        elif ch in ")]}>":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur)
+    return out
+
+
+def test_rust_wrapper_matches_the_header_and_covers_every_interpolator():
+    # integration/rust/ninterp/src/cuda.rs (source only): every sys:: call names a declared function and passes as
+    # many arguments as the header takes; every sys:: constant exists; every interpolator of the reference gets
+    # to_cuda; the ExtrapolateError text is the reference's
+    header = (ROOT / "include" / "ninterp_cuda.h").read_text()
+    wrapper = (ROOT / "integration" / "rust" / "ninterp" / "src" / "cuda.rs").read_text()
+    declared = _declared()
+    calls = 0
+    for m in re.finditer(r"sys::(nint_\w+)\s*\(", wrapper):
+        name = m.group(1)
+        assert name in declared, f"{name} is not in include/ninterp_cuda.h"
+        depth, i = 1, m.end()
+        while depth:
+            depth += {"(": 1, ")": -1}.get(wrapper[i], 0)
+            i += 1
+        n_rust = len(_split_args(wrapper[m.end():i - 1]))
+        c_args = re.search(r"\b%s\s*\(([^)]*)\)" % name, header, flags=re.S).group(1)
+        n_c = 0 if c_args.strip() in ("", "void") else c_args.count(",") + 1
+        assert n_c == n_rust, f"{name}: {n_c} arguments in C, {n_rust} in the Rust call"
+        calls += 1
+    assert calls >= 9
+    for const in set(re.findall(r"sys::(NINT_[A-Z0-9_]+)", wrapper)):
+        assert re.search(r"\b%s\b" % const, header), f"{const} is not in the header"
+    for interp, strat in (("Interp1D", "Strategy1D"), ("Interp2D", "Strategy2D"), ("Interp3D", "Strategy3D"), ("InterpND", "StrategyND")):
+        assert re.search(r"to_cuda_impl!\(%s, %s, sys::NINT_KIND_(FIXED|ND)\)" % (interp, strat), wrapper), interp
+    assert "to_cuda_impl!(InterpND, StrategyND, sys::NINT_KIND_ND)" in wrapper
+    assert "impl<D> InterpolatorEnum<D>" in wrapper and "InterpolatorEnum::Interp0D(i) => CudaInterpolator::Constant" in wrapper
+    for strat in ("Linear", "Nearest", "LeftNearest", "RightNearest", "Strategy1DEnum"):
+        assert f"impl CudaStrategy for strategy::{'enums::' if strat.endswith('Enum') else ''}{strat}" in wrapper
+    assert "two_variant_enum!(Strategy2DEnum, Strategy3DEnum, StrategyNDEnum)" in wrapper
+    # three/mod.rs:226-229, one/mod.rs:198-203, n/mod.rs:326-329
+    assert 'format!("\\n    point[{dim}] = {:?} is out of bounds for grid[{dim}] = {:?}", point[dim], g)' in wrapper
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
 
