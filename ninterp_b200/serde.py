@@ -71,6 +71,7 @@ def to_json(interp) -> str:
         return {"v": 1, "dim": list(a.shape), "data": a.reshape(-1).tolist()}
 
     e = interp.extrapolate
-    ext = {"Fill": e.value} if repr(e).startswith("Fill") else repr(e)
+    # serde_json has no NaN: a NaN fill value is written as null
+    ext = {"Fill": None if e.value != e.value else e.value} if repr(e).startswith("Fill") else repr(e)
     return json.dumps({"data": {"grid": [arr(g) for g in interp.data.grid], "values": arr(interp.data.values)},
                        "strategy": repr(interp.strategy), "extrapolate": ext})

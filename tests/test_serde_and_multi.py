@@ -26,6 +26,54 @@ def test_json_parsing_needs_no_gpu():
     assert serde.from_json("0.5").interpolate([]) == 0.5          # Interp0D is a bare number (zero/mod.rs:11)
 
 
+GOLDEN = __import__("pathlib").Path(__file__).resolve().parent / "golden"
+
+
+def test_golden_fixtures_are_reproducible_and_parse():
+    # tests/golden/*.json are written by tests/golden/make_serde_fixtures.py from the reference's serde attributes and
+    # serde tests (the crate itself cannot run here); regenerate and compare, then parse without a GPU
+    import subprocess
+    import sys
+
+    before = {f.name: f.read_text() for f in GOLDEN.glob("*.json")}
+    subprocess.run([sys.executable, str(GOLDEN / "make_serde_fixtures.py")], check=True)
+    assert before == {f.name: f.read_text() for f in GOLDEN.glob("*.json")} and len(before) == 5
+    from ninterp_b200 import serde
+
+    doc = json.loads(before["serde_enums_rs_2d_nearest.json"])
+    assert doc["strategy"] == "Nearest" and doc["extrapolate"] == "Error"      # untagged Strategy2DEnum == bare name
+    assert serde._array(doc["data"]["values"], np.float64).shape == (3, 3)
+    assert np.isnan(serde._extrapolate(json.loads(before["serde_one_fill_nan.json"])["extrapolate"]).value)
+    assert "extrapolate" not in json.loads(before["serde_one_default_extrapolate.json"])
+    assert serde.from_json(before["serde_interp0d.json"]).interpolate([]) == 0.5
+
+
+@pytest.mark.gpu
+def test_golden_serde_fixtures_evaluate_like_the_reference():
+    import ninterp_b200 as nb
+
+    # enums.rs:362-373: Interp2D, InterpND and both InterpolatorEnum wrappings serialise to one string, so one fixture
+    # loads as each of them; values from two/tests.rs:79-93 (Nearest, incl. the "float imprecision" case)
+    text = (GOLDEN / "serde_enums_rs_2d_nearest.json").read_text()
+    for kind, cls in (("auto", nb.Interp2D), ("fixed", nb.Interp2D), ("nd", nb.InterpND)):
+        g = nb.from_json(text, kind=kind)
+        assert isinstance(g, cls) and g.ndim() == 2
+        assert g.interpolate([0.05, 0.12]) == 0.0 and g.interpolate([0.07, 0.15 + 0.0001]) == 1.0
+        assert g.interpolate([0.08, 0.21]) == 4.0 and g.interpolate([0.14, 0.29]) == 8.0
+        with pytest.raises(nb.InterpolateError):
+            g.interpolate([0.2, 0.2])
+        assert json.loads(nb.to_json(g)) == json.loads(text)
+    g = nb.from_json((GOLDEN / "serde_three_tests_nearest.json").read_text())
+    assert isinstance(g, nb.Interp3D) and g.interpolate([0.75, 0.25, 0.75]) == 5.0   # three/tests.rs:124
+    g = nb.from_json((GOLDEN / "serde_one_fill_nan.json").read_text())              # one/tests.rs:134-147
+    assert g.interpolate([1.5]) == 0.5 and g.interpolate([2.0]) == 0.6
+    assert np.isnan(g.interpolate([-1.0])) and np.isnan(g.interpolate([5.0]))
+    g = nb.from_json((GOLDEN / "serde_one_default_extrapolate.json").read_text())
+    assert g.interpolate([1.5]) == 0.4                                              # LeftNearest
+    with pytest.raises(nb.InterpolateError):
+        g.interpolate([5.0])                                                        # default Extrapolate::Error
+
+
 @pytest.mark.gpu
 def test_from_json_round_trip_and_values():
     import ninterp_b200 as nb
