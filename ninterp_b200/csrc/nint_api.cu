@@ -615,7 +615,12 @@ void build_tile(nint_handle* h) {
     if (const char* env = std::getenv("NINT_TILE_SC_SHIFT")) sc_shift = (unsigned)std::atoi(env);
     g.sc_shift = std::min(28u, std::max(10u, sc_shift));
     const unsigned long long per_list = (1ull << g.sc_shift) / ntiles;
-    g.cap = (unsigned)((per_list + per_list / 4 + 256 + 31) / 32 * 32);
+    unsigned page_shift = 6;  // 64 records = 2 KB per page
+    if (const char* env = std::getenv("NINT_TILE_PAGE_SHIFT")) page_shift = (unsigned)std::atoi(env);
+    g.page_shift = std::min(20u, std::max(2u, page_shift));
+    const unsigned long long page = 1ull << g.page_shift;
+    g.rounds = (unsigned)((per_list + per_list / 4 + 256 + page - 1) / page);
+    g.cap = g.rounds << g.page_shift;
 
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -713,7 +718,8 @@ int launch_tiles(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
         G.n_sc = (unsigned)((m + (1ull << G.sc_shift) - 1) >> G.sc_shift);
         cudaError_t e = cudaMemsetAsync(G.cursor, 0, (size_t)G.n_sc * (size_t)G.ntiles * nint::kCursorStride * sizeof(unsigned), stream);
         if (e == cudaSuccess) e = nint::launch_tile_bin<T>(P, G, tl);
-        if (e == cudaSuccess) {
+        static const bool bin_only = std::getenv("NINT_TILE_BIN_ONLY") != nullptr;  // measurement: results are NOT produced
+        if (e == cudaSuccess && !bin_only) {
             nint::TileEval<T> E;
             E.out = P.out;
             E.mode_flag = P.mode_flag;

@@ -25,7 +25,6 @@
 
 namespace nint {
 
-constexpr int kTileThreads = 1024;      // tile_eval_kernel: one CTA per SM (two tile buffers fill its shared memory)
 constexpr unsigned kCursorStride = 8;   // u32 slots between list cursors: 32 bytes, so neighbours hit different L2 slices
 constexpr int kTileRecBytes = 32;
 
@@ -37,12 +36,22 @@ struct TileGeom {
     int box[3];           // staged elements per axis: cells per tile + 1 (innermost padded to a 16-byte multiple)
     unsigned tile_bytes;  // bytes TMA delivers per tile (box volume x sizeof(T))
     unsigned buf_bytes;   // tile_bytes rounded up to 128
-    unsigned cap;         // records per (superchunk, tile) list
+    unsigned cap;         // records per (superchunk, tile) list: rounds << page_shift
+    unsigned page_shift;  // log2(records per page).  A list is stored as pages interleaved over the tiles of its
+    unsigned rounds;      // superchunk: page r of every tile, then page r + 1, ...  Lists grow at the same pace when the
+                          // queries are spread evenly, so the appends of a moment land in a few MB instead of one spot
+                          // per list over hundreds of MB (one TLB miss per 32-byte record otherwise)
     unsigned sc_shift;    // log2(points per superchunk)
     unsigned n_sc;        // superchunks in this launch
     unsigned* cursor;     // [n_sc * ntiles] list lengths, kCursorStride apart
     unsigned char* records;  // [n_sc * ntiles][cap] records of kTileRecBytes
 };
+
+// Byte offset of record `slot` of list (sc, tile).
+__device__ __forceinline__ size_t record_offset(const TileGeom& G, unsigned sc, unsigned tile, unsigned slot) {
+    const size_t page = ((size_t)sc * G.rounds + (slot >> G.page_shift)) * (size_t)G.ntiles + tile;
+    return ((page << G.page_shift) + (slot & ((1u << G.page_shift) - 1u))) * (size_t)kTileRecBytes;
+}
 
 // First half of fast_point() for Linear: cell guess, verification and weights of every axis.  Same functions, same
 // order, so a point is accepted here exactly when the single pass accepts it, with the same k and t.
@@ -169,10 +178,11 @@ __global__ void __launch_bounds__(kBlock, 4) tile_bin_kernel(const __grid_consta
             const unsigned tile = (unsigned)(((k[0] >> G.sh[0]) * G.nt[1] + (k[1] >> G.sh[1])) * G.nt[2] + (k[2] >> G.sh[2]));
             const unsigned loc = (unsigned)(k[0] & ((1 << G.sh[0]) - 1)) | ((unsigned)(k[1] & ((1 << G.sh[1]) - 1)) << 8) |
                                  ((unsigned)(k[2] & ((1 << G.sh[2]) - 1)) << 16);
-            const unsigned list = (i >> G.sc_shift) * (unsigned)G.ntiles + tile;
+            const unsigned sc = i >> G.sc_shift;
+            const unsigned list = sc * (unsigned)G.ntiles + tile;
             const unsigned slot = atomicAdd(G.cursor + (size_t)list * kCursorStride, 1u);
             if (slot < G.cap) {
-                st_record(G.records + ((size_t)list * G.cap + slot) * kTileRecBytes, t[0], t[1], t[2], i, loc);
+                st_record(G.records + record_offset(G, sc, tile, slot), t[0], t[1], t[2], i, loc);
             } else {
                 // list full (queries far from uniform): finish the point here from the plain table
                 long long base = 0;
@@ -268,6 +278,16 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map,
         : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Contiguous global -> shared copy by the TMA engine (UBLKCP); size and both addresses are multiples of 16.
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 template <class T>
 struct TileEval {
     T* out;
@@ -275,22 +295,40 @@ struct TileEval {
     int mode_want;
 };
 
+// One CTA per SM: warp 0 is the producer (one lane drives the TMA engine), kEvalConsumers threads evaluate.
+//   tile ring    2 buffers   producer: UTMALDG of the item's tile        consumers: corner loads (LDS)
+//   record ring  kEvalStages buffers of kEvalChunk records, UBLKCP page by page; one record per consumer thread
+// Every buffer has a `full` (transaction-count) and an `empty` (one arrival per consumer warp) mbarrier, so record
+// and tile traffic of the items ahead is in flight while the current records are blended: nothing waits on DRAM
+// latency.  Both roles walk the same item sequence (the lists are complete before this kernel starts).
+constexpr int kEvalConsumers = 512;
+constexpr int kEvalThreads = kEvalConsumers + 32;
+constexpr int kEvalStages = 3;
+constexpr int kEvalChunk = kEvalConsumers;  // records per stage
+
 template <class T>
-__global__ void __launch_bounds__(kTileThreads, 1) tile_eval_kernel(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                      const __grid_constant__ TileEval<T> E,
                                                                      const __grid_constant__ TileGeom G) {
     constexpr int N = 3;
-    constexpr int kUnroll = 4;
-    extern __shared__ __align__(128) unsigned char smem_tiles[];
-    __shared__ __align__(8) unsigned long long s_bar[2];
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    __shared__ __align__(8) unsigned long long tile_full[2], tile_empty[2], rec_full[kEvalStages], rec_empty[kEvalStages];
     if (E.mode_flag != nullptr && *E.mode_flag != E.mode_want) return;
     const unsigned tid = threadIdx.x;
+    unsigned char* const tiles = smem_dyn;
+    unsigned char* const stages = smem_dyn + 2u * G.buf_bytes;
     if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tile_full[b], 1);
+            mbar_init(&tile_empty[b], kEvalConsumers / 32);
+        }
+        for (int s = 0; s < kEvalStages; ++s) {
+            mbar_init(&rec_full[s], 1);
+            mbar_init(&rec_empty[s], kEvalConsumers / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    __syncthreads();  // the only CTA-wide barrier: the roles part here
 
     const unsigned nitems = G.n_sc * (unsigned)G.ntiles;
     // this CTA's items: blockIdx.x, + gridDim.x, ...: superchunk-major, so that at any time all CTAs scatter into
@@ -299,60 +337,88 @@ __global__ void __launch_bounds__(kTileThreads, 1) tile_eval_kernel(const __grid
         while (j < nitems && G.cursor[(size_t)j * kCursorStride] == 0u) j += gridDim.x;
         return j;
     };
-    auto issue = [&](unsigned item, unsigned b) {
-        const int tile = (int)(item % (unsigned)G.ntiles);
-        const int t2 = tile % G.nt[2];
-        const int t1 = (tile / G.nt[2]) % G.nt[1];
-        const int t0 = tile / (G.nt[2] * G.nt[1]);
-        mbar_expect_tx(&s_bar[b], G.tile_bytes);
-        tma_load_tile(smem_tiles + (size_t)b * G.buf_bytes, &tmap, &s_bar[b], t2 << G.sh[2], t1 << G.sh[1], t0 << G.sh[0]);
-    };
-    const int sy = G.box[2];
-    const int sx = G.box[1] * G.box[2];
 
-    unsigned cur = next_item(blockIdx.x);
-    unsigned b = 0;
-    unsigned parity[2] = {0u, 0u};
-    if (tid == 0 && cur < nitems) issue(cur, 0);
-    while (cur < nitems) {
-        const unsigned nxt = next_item(cur + gridDim.x);
-        __syncthreads();  // every thread is done with the other buffer (the previous item's tile)
-        if (tid == 0 && nxt < nitems) issue(nxt, b ^ 1u);
-        const unsigned count = min(G.cursor[(size_t)cur * kCursorStride], G.cap);
-        const unsigned char* recs = G.records + (size_t)cur * G.cap * kTileRecBytes;
-        // the tile was requested one item ago and has normally landed by now
-        mbar_wait(&s_bar[b], parity[b]);
-        parity[b] ^= 1u;
-        const T* tile = reinterpret_cast<const T*>(smem_tiles + (size_t)b * G.buf_bytes);
-        for (unsigned base = 0; base < count; base += kTileThreads * kUnroll) {
-            T t[kUnroll][N];
-            unsigned idx[kUnroll], loc[kUnroll];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const unsigned r = base + u * kTileThreads + tid;
-                if (r < count) ld_record(recs + (size_t)r * kTileRecBytes, t[u][0], t[u][1], t[u][2], idx[u], loc[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const unsigned r = base + u * kTileThreads + tid;
-                if (r < count) {
-                    const int off = (int)(loc[u] & 0xffu) * sx + (int)((loc[u] >> 8) & 0xffu) * sy + (int)(loc[u] >> 16);
-                    const T* c = tile + off;
-                    T cube[1 << N];
-                    cube[0] = c[0];
-                    cube[1] = c[1];
-                    cube[2] = c[sy];
-                    cube[3] = c[sy + 1];
-                    cube[4] = c[sx];
-                    cube[5] = c[sx + 1];
-                    cube[6] = c[sx + sy];
-                    cube[7] = c[sx + sy + 1];
-                    E.out[idx[u]] = blend_cube<T, N>(cube, t[u]);
+    if (tid < 32) {
+        if (tid != 0) return;
+        // ---------------------------------------------------------------- producer
+        unsigned tb = 0, tb_phase = 0, st = 0, st_phase = 0;
+        for (unsigned item = next_item(blockIdx.x); item < nitems; item = next_item(item + gridDim.x)) {
+            const unsigned sc = item / (unsigned)G.ntiles;
+            const unsigned tile = item - sc * (unsigned)G.ntiles;
+            const int t2 = (int)tile % G.nt[2];
+            const int t1 = ((int)tile / G.nt[2]) % G.nt[1];
+            const int t0 = (int)tile / (G.nt[2] * G.nt[1]);
+            mbar_wait(&tile_empty[tb], tb_phase ^ 1u);
+            mbar_expect_tx(&tile_full[tb], G.tile_bytes);
+            tma_load_tile(tiles + (size_t)tb * G.buf_bytes, &tmap, &tile_full[tb], t2 << G.sh[2], t1 << G.sh[1], t0 << G.sh[0]);
+            tb ^= 1u;
+            tb_phase ^= (tb == 0u);
+            const unsigned count = min(G.cursor[(size_t)item * kCursorStride], G.cap);
+            for (unsigned base = 0; base < count; base += kEvalChunk) {
+                const unsigned m = min((unsigned)kEvalChunk, count - base);
+                mbar_wait(&rec_empty[st], st_phase ^ 1u);
+                mbar_expect_tx(&rec_full[st], m * kTileRecBytes);
+                unsigned char* dst = stages + (size_t)st * (kEvalChunk * kTileRecBytes);
+                // page by page: a piece never crosses a page boundary
+                for (unsigned slot = base; slot < base + m;) {
+                    const unsigned in_page = slot & ((1u << G.page_shift) - 1u);
+                    const unsigned len = min((1u << G.page_shift) - in_page, base + m - slot);
+                    bulk_load(dst + (size_t)(slot - base) * kTileRecBytes, G.records + record_offset(G, sc, tile, slot),
+                              len * kTileRecBytes, &rec_full[st]);
+                    slot += len;
+                }
+                if (++st == kEvalStages) {
+                    st = 0;
+                    st_phase ^= 1u;
                 }
             }
         }
-        cur = nxt;
-        b ^= 1u;
+        return;
+    }
+    // -------------------------------------------------------------------- consumers
+    const unsigned ct = tid - 32u;
+    const unsigned lane = tid & 31u;
+    const int sy = G.box[2];
+    const int sx = G.box[1] * G.box[2];
+    unsigned tb = 0, tb_phase = 0, st = 0, st_phase = 0;
+    for (unsigned item = next_item(blockIdx.x); item < nitems; item = next_item(item + gridDim.x)) {
+        const unsigned count = min(G.cursor[(size_t)item * kCursorStride], G.cap);
+        mbar_wait(&tile_full[tb], tb_phase);
+        const T* tile = reinterpret_cast<const T*>(tiles + (size_t)tb * G.buf_bytes);
+        for (unsigned base = 0; base < count; base += kEvalChunk) {
+            const unsigned m = min((unsigned)kEvalChunk, count - base);
+            mbar_wait(&rec_full[st], st_phase);
+            if (ct < m) {
+                const unsigned char* rp = stages + (size_t)st * (kEvalChunk * kTileRecBytes) + (size_t)ct * kTileRecBytes;
+                const double2 r0 = *reinterpret_cast<const double2*>(rp);
+                const double2 r1 = *reinterpret_cast<const double2*>(rp + 16);
+                T t[N] = {(T)r0.x, (T)r0.y, (T)r1.x};
+                const unsigned long long meta = (unsigned long long)__double_as_longlong(r1.y);
+                const unsigned idx = (unsigned)meta, loc = (unsigned)(meta >> 32);
+                const int off = (int)(loc & 0xffu) * sx + (int)((loc >> 8) & 0xffu) * sy + (int)(loc >> 16);
+                const T* c = tile + off;
+                T cube[1 << N];
+                cube[0] = c[0];
+                cube[1] = c[1];
+                cube[2] = c[sy];
+                cube[3] = c[sy + 1];
+                cube[4] = c[sx];
+                cube[5] = c[sx + 1];
+                cube[6] = c[sx + sy];
+                cube[7] = c[sx + sy + 1];
+                E.out[idx] = blend_cube<T, N>(cube, t);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rec_empty[st]);
+            if (++st == kEvalStages) {
+                st = 0;
+                st_phase ^= 1u;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tile_empty[tb]);
+        tb ^= 1u;
+        tb_phase ^= (tb == 0u);
     }
 }
 

@@ -58,14 +58,14 @@ template <>
 cudaError_t launch_tile_eval<NINT_T>(const CUtensorMap& tmap, const TileEval<NINT_T>& E, const TileGeom& G,
                                      const TileLaunch& cfg) {
     auto kern = tile_eval_kernel<NINT_T>;
-    const unsigned smem = 2u * G.buf_bytes;
+    const unsigned smem = 2u * G.buf_bytes + (unsigned)(kEvalStages * kEvalChunk * kTileRecBytes);
     static thread_local unsigned configured = 0;
     if (configured < smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    kern<<<(unsigned)cfg.sm_count, kTileThreads, smem, (cudaStream_t)cfg.stream>>>(tmap, E, G);
+    kern<<<(unsigned)cfg.sm_count, kEvalThreads, smem, (cudaStream_t)cfg.stream>>>(tmap, E, G);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
