@@ -618,6 +618,7 @@ void build_tile(nint_handle* h) {
     unsigned page_shift = 6;  // 64 records = 2 KB per page
     if (const char* env = std::getenv("NINT_TILE_PAGE_SHIFT")) page_shift = (unsigned)std::atoi(env);
     g.page_shift = std::min(20u, std::max(2u, page_shift));
+    if (const char* env = std::getenv("NINT_TILE_FLAGS")) g.flags = (unsigned)std::atoi(env);
     const unsigned long long page = 1ull << g.page_shift;
     g.rounds = (unsigned)((per_list + per_list / 4 + 256 + page - 1) / page);
     g.cap = g.rounds << g.page_shift;

@@ -43,6 +43,8 @@ struct TileGeom {
                           // per list over hundreds of MB (one TLB miss per 32-byte record otherwise)
     unsigned sc_shift;    // log2(points per superchunk)
     unsigned n_sc;        // superchunks in this launch
+    unsigned flags;       // tuning (NINT_TILE_FLAGS): 1 = record stores evict-first, 2 = no evict-first hint on the record
+                          // and tile loads, 4 = no evict-last hint on the result stores
     unsigned* cursor;     // [n_sc * ntiles] list lengths, kCursorStride apart
     unsigned char* records;  // [n_sc * ntiles][cap] records of kTileRecBytes
 };
@@ -98,9 +100,17 @@ __device__ __forceinline__ T blend_cube(T (&cube)[1 << N], const T (&t)[N]) {
     return cube[0];
 }
 
-__device__ __forceinline__ void st_record(unsigned char* dst, double t0, double t1, double t2, unsigned idx, unsigned loc) {
+__device__ __forceinline__ void st_record_cs(unsigned char* dst, double t0, double t1, double t2, unsigned idx, unsigned loc) {
     const unsigned long long meta = (unsigned long long)idx | ((unsigned long long)loc << 32);
     asm volatile("st.global.cs.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "l"(__double_as_longlong(t0)),
+                 "l"(__double_as_longlong(t1)), "l"(__double_as_longlong(t2)), "l"(meta)
+                 : "memory");
+}
+__device__ __forceinline__ void st_record(unsigned char* dst, double t0, double t1, double t2, unsigned idx, unsigned loc) {
+    const unsigned long long meta = (unsigned long long)idx | ((unsigned long long)loc << 32);
+    // default L2 priority: the 2 KB page a list is filling stays in L2 until its lines are complete (evict-first
+    // sectors leave one by one and turn into partial-line DRAM writes)
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "l"(__double_as_longlong(t0)),
                  "l"(__double_as_longlong(t1)), "l"(__double_as_longlong(t2)), "l"(meta)
                  : "memory");
 }
@@ -182,7 +192,8 @@ __global__ void __launch_bounds__(kBlock, 4) tile_bin_kernel(const __grid_consta
             const unsigned list = sc * (unsigned)G.ntiles + tile;
             const unsigned slot = atomicAdd(G.cursor + (size_t)list * kCursorStride, 1u);
             if (slot < G.cap) {
-                st_record(G.records + record_offset(G, sc, tile, slot), t[0], t[1], t[2], i, loc);
+                if (G.flags & 1u) st_record_cs(G.records + record_offset(G, sc, tile, slot), (double)t[0], (double)t[1], (double)t[2], i, loc);
+                else st_record(G.records + record_offset(G, sc, tile, slot), t[0], t[1], t[2], i, loc);
             } else {
                 // list full (queries far from uniform): finish the point here from the plain table
                 long long base = 0;
@@ -270,11 +281,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 // One tile: box (box[2], box[1], box[0]) of the table at element coordinates (c0 innermost) -> shared memory.
 __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1,
-                                              int c2) {
+                                              int c2, unsigned long long pol) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
             smem_u32(dst)),
-        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(pol)
         : "memory");
 }
 
@@ -282,10 +293,28 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Contiguous global -> shared copy by the TMA engine (UBLKCP); size and both addresses are multiples of 16.
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar,
+                                          unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                  : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_hint(double* p, double v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(float* p, float v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
 }
 
 template <class T>
@@ -303,7 +332,7 @@ struct TileEval {
 // latency.  Both roles walk the same item sequence (the lists are complete before this kernel starts).
 constexpr int kEvalConsumers = 512;
 constexpr int kEvalThreads = kEvalConsumers + 32;
-constexpr int kEvalStages = 3;
+constexpr int kEvalStages = 4;
 constexpr int kEvalChunk = kEvalConsumers;  // records per stage
 
 template <class T>
@@ -341,6 +370,9 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
     if (tid < 32) {
         if (tid != 0) return;
         // ---------------------------------------------------------------- producer
+        // records and tiles are used once per superchunk: evict-first, so that the window of `out` the superchunk
+        // scatters into (8 bytes x 2^sc_shift) stays in L2 until its sectors are complete
+        const unsigned long long stream_pol = (G.flags & 2u) ? make_table_policy(0.0f) : l2_policy_evict_first();
         unsigned tb = 0, tb_phase = 0, st = 0, st_phase = 0;
         for (unsigned item = next_item(blockIdx.x); item < nitems; item = next_item(item + gridDim.x)) {
             const unsigned sc = item / (unsigned)G.ntiles;
@@ -350,7 +382,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
             const int t0 = (int)tile / (G.nt[2] * G.nt[1]);
             mbar_wait(&tile_empty[tb], tb_phase ^ 1u);
             mbar_expect_tx(&tile_full[tb], G.tile_bytes);
-            tma_load_tile(tiles + (size_t)tb * G.buf_bytes, &tmap, &tile_full[tb], t2 << G.sh[2], t1 << G.sh[1], t0 << G.sh[0]);
+            tma_load_tile(tiles + (size_t)tb * G.buf_bytes, &tmap, &tile_full[tb], t2 << G.sh[2], t1 << G.sh[1], t0 << G.sh[0], stream_pol);
             tb ^= 1u;
             tb_phase ^= (tb == 0u);
             const unsigned count = min(G.cursor[(size_t)item * kCursorStride], G.cap);
@@ -364,7 +396,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
                     const unsigned in_page = slot & ((1u << G.page_shift) - 1u);
                     const unsigned len = min((1u << G.page_shift) - in_page, base + m - slot);
                     bulk_load(dst + (size_t)(slot - base) * kTileRecBytes, G.records + record_offset(G, sc, tile, slot),
-                              len * kTileRecBytes, &rec_full[st]);
+                              len * kTileRecBytes, &rec_full[st], stream_pol);
                     slot += len;
                 }
                 if (++st == kEvalStages) {
@@ -380,6 +412,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
     const unsigned lane = tid & 31u;
     const int sy = G.box[2];
     const int sx = G.box[1] * G.box[2];
+    const unsigned long long keep_pol = (G.flags & 4u) ? make_table_policy(0.0f) : l2_policy_evict_last();
     unsigned tb = 0, tb_phase = 0, st = 0, st_phase = 0;
     for (unsigned item = next_item(blockIdx.x); item < nitems; item = next_item(item + gridDim.x)) {
         const unsigned count = min(G.cursor[(size_t)item * kCursorStride], G.cap);
@@ -406,7 +439,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
                 cube[5] = c[sx + 1];
                 cube[6] = c[sx + sy];
                 cube[7] = c[sx + sy + 1];
-                E.out[idx] = blend_cube<T, N>(cube, t);
+                st_hint(E.out + idx, blend_cube<T, N>(cube, t), keep_pol);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&rec_empty[st]);
