@@ -44,7 +44,7 @@ struct TileGeom {
     unsigned sc_shift;    // log2(points per superchunk)
     unsigned n_sc;        // superchunks in this launch
     unsigned flags;       // tuning (NINT_TILE_FLAGS): 1 = record stores evict-first, 2 = no evict-first hint on the record
-                          // and tile loads, 4 = no evict-last hint on the result stores
+                          // and tile loads, 4 = no evict-last hint on the result stores, 8 = no result stores at all (measurement only)
     unsigned* cursor;     // [n_sc * ntiles] list lengths, kCursorStride apart
     unsigned char* records;  // [n_sc * ntiles][cap] records of kTileRecBytes
 };
@@ -374,17 +374,26 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
         // scatters into (8 bytes x 2^sc_shift) stays in L2 until its sectors are complete
         const unsigned long long stream_pol = (G.flags & 2u) ? make_table_policy(0.0f) : l2_policy_evict_first();
         unsigned tb = 0, tb_phase = 0, st = 0, st_phase = 0;
-        for (unsigned item = next_item(blockIdx.x); item < nitems; item = next_item(item + gridDim.x)) {
-            const unsigned sc = item / (unsigned)G.ntiles;
-            const unsigned tile = item - sc * (unsigned)G.ntiles;
-            const int t2 = (int)tile % G.nt[2];
-            const int t1 = ((int)tile / G.nt[2]) % G.nt[1];
-            const int t0 = (int)tile / (G.nt[2] * G.nt[1]);
+        // the tile of the NEXT item is requested before the records of the current one: the record stages only free
+        // up as the consumers work through the item, and a tile requested after them would land too late
+        auto request_tile = [&](unsigned item) {
+            const int tile = (int)(item % (unsigned)G.ntiles);
+            const int t2 = tile % G.nt[2];
+            const int t1 = (tile / G.nt[2]) % G.nt[1];
+            const int t0 = tile / (G.nt[2] * G.nt[1]);
             mbar_wait(&tile_empty[tb], tb_phase ^ 1u);
             mbar_expect_tx(&tile_full[tb], G.tile_bytes);
             tma_load_tile(tiles + (size_t)tb * G.buf_bytes, &tmap, &tile_full[tb], t2 << G.sh[2], t1 << G.sh[1], t0 << G.sh[0], stream_pol);
             tb ^= 1u;
             tb_phase ^= (tb == 0u);
+        };
+        unsigned item = next_item(blockIdx.x);
+        if (item < nitems) request_tile(item);
+        while (item < nitems) {
+            const unsigned nxt = next_item(item + gridDim.x);
+            if (nxt < nitems) request_tile(nxt);
+            const unsigned sc = item / (unsigned)G.ntiles;
+            const unsigned tile = item - sc * (unsigned)G.ntiles;
             const unsigned count = min(G.cursor[(size_t)item * kCursorStride], G.cap);
             for (unsigned base = 0; base < count; base += kEvalChunk) {
                 const unsigned m = min((unsigned)kEvalChunk, count - base);
@@ -404,6 +413,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
                     st_phase ^= 1u;
                 }
             }
+            item = nxt;
         }
         return;
     }
@@ -439,7 +449,8 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
                 cube[5] = c[sx + 1];
                 cube[6] = c[sx + sy];
                 cube[7] = c[sx + sy + 1];
-                st_hint(E.out + idx, blend_cube<T, N>(cube, t), keep_pol);
+                const T value = blend_cube<T, N>(cube, t);
+                if (!(G.flags & 8u) || idx == 0xffffffffu) st_hint(E.out + idx, value, keep_pol);  // 8: measurement without the scatter
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&rec_empty[st]);
