@@ -89,7 +89,7 @@ const char* extrap_name(int e) {
 struct AxisMeta {
     int L = 0, M = 0;
     unsigned node_off = 0, lut_off = 0, guess_off = 0;
-    double g0 = 0, gl = 0, inv_w = 0, inv_h = 0;
+    double g0 = 0, gl = 0, inv_w = 0, inv_h = 0, h = 0;
     int flags = 0;
     long long vstride = 0;
     long long cstride = 0;  // stride of this axis in the cell-packed table, in cells
@@ -276,6 +276,33 @@ void classify_axis(const nint_handle* h, int d, AxisMeta& a) {
         if (uniform && std::isfinite(inv_h) && inv_h > 0.0) {
             a.flags |= nint::kAxisUniform;
             a.inv_h = inv_h;
+            // analytic: every node equals g0 + k * h bit for bit, evaluated in T with one rounding per operation
+            // (what `arange(L) * h` and `linspace` produce); candidates for h: the first cell, the mean cell
+            for (int cand = 0; cand < 2 && !(a.flags & nint::kAxisAnalytic); ++cand) {
+                bool exact = true;
+                if (h->dtype == NINT_F64) {
+                    const double* g = (const double*)nodes;
+                    const double hc = cand == 0 ? g[1] - g[0] : (g[L - 1] - g[0]) / (double)(L - 1);
+                    for (int i = 0; i < L && exact; ++i) {
+                        volatile double kh = (double)i * hc;
+                        volatile double v = g[0] + kh;
+                        exact = (v == g[i]);
+                    }
+                    if (exact && hc > 0.0) a.h = hc;
+                    else exact = false;
+                } else {
+                    const float* g = (const float*)nodes;
+                    const float hc = cand == 0 ? g[1] - g[0] : (g[L - 1] - g[0]) / (float)(L - 1);
+                    for (int i = 0; i < L && exact; ++i) {
+                        volatile float kh = (float)i * hc;
+                        volatile float v = g[0] + kh;
+                        exact = (v == g[i]);
+                    }
+                    if (exact && hc > 0.0f) a.h = (double)hc;
+                    else exact = false;
+                }
+                if (exact) a.flags |= nint::kAxisAnalytic;
+            }
         }
     }
 }
@@ -517,6 +544,7 @@ void fill_params(const nint_handle* h, nint::Params<T>& P) {
         P.gl[d] = (T)a.gl;
         P.inv_w[d] = (T)a.inv_w;
         P.inv_h[d] = (T)a.inv_h;
+        P.h[d] = (T)a.h;
         P.flags[d] = a.flags;
     }
 }
@@ -700,6 +728,10 @@ int launch_tiles(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
     nint::TileLaunch tl;
     tl.is_nd = cfg.is_nd;
     tl.all_uniform = cfg.all_uniform;
+    tl.all_analytic = 1;
+    for (int d = 0; d < h->ndim_eff; ++d)
+        if (!(h->ax[d].flags & nint::kAxisAnalytic)) tl.all_analytic = 0;
+    if (std::getenv("NINT_NO_ANALYTIC")) tl.all_analytic = 0;
     tl.sm_count = cfg.sm_count;
     tl.smem_bytes = cfg.smem_bytes;
     tl.stream = stream;
@@ -723,6 +755,7 @@ int launch_tiles(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
         if (e == cudaSuccess && !bin_only) {
             nint::TileEval<T> E;
             E.out = P.out;
+            E.n = (unsigned)m;
             E.mode_flag = P.mode_flag;
             E.mode_want = P.mode_want;
             e = nint::launch_tile_eval<T>(h->tile_map, E, G, tl);

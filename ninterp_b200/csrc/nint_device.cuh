@@ -44,6 +44,7 @@ constexpr int kAxisUniform = 1;  // nodes are evenly spaced to within a small fr
 constexpr int kModeCoherent = 1;  // consecutive queries mostly fall into neighbouring cells
 constexpr int kModeRandom = 2;    // they do not: evaluate in slab passes
 
+constexpr int kAxisAnalytic = 4;  // uniform axis whose nodes are, bit for bit, g[k] = g0 + k * h in T (two roundings)
 constexpr int kAxisFast = 2;     // axis may use the fast path: >= 2 nodes, strictly increasing, every cell
                                  // width inside the division window (all reciprocals stored)
 
@@ -81,6 +82,7 @@ struct Params {
     T g0[kMaxDim], gl[kMaxDim];
     T inv_w[kMaxDim];            // buckets per unit length (guess table and {lo, hi} table share the buckets)
     T inv_h[kMaxDim];            // cells per unit length (uniform axes)
+    T h[kMaxDim];                // cell width of an analytic axis (kAxisAnalytic): g[k] == g0 + k * h exactly
 };
 
 template <class T>

@@ -44,7 +44,7 @@ struct TileGeom {
     unsigned sc_shift;    // log2(points per superchunk)
     unsigned n_sc;        // superchunks in this launch
     unsigned flags;       // tuning (NINT_TILE_FLAGS): 1 = record stores evict-first, 2 = no evict-first hint on the record
-                          // and tile loads, 4 = no evict-last hint on the result stores, 8 = no result stores at all (measurement only)
+                          // and tile loads, 4 = no evict-last hint on the result stores, 8 = no result stores at all (measurement only), 16 = no prefetch of the result window
     unsigned* cursor;     // [n_sc * ntiles] list lengths, kCursorStride apart
     unsigned char* records;  // [n_sc * ntiles][cap] records of kTileRecBytes
 };
@@ -57,6 +57,33 @@ __device__ __forceinline__ size_t record_offset(const TileGeom& G, unsigned sc, 
 
 // First half of fast_point() for Linear: cell guess, verification and weights of every axis.  Same functions, same
 // order, so a point is accepted here exactly when the single pass accepts it, with the same k and t.
+// The same for axes whose nodes are exactly g0 + k * h (checked bit for bit on the host, Params::h): the two nodes of
+// the guessed cell are computed instead of loaded, and t = a / w is the IEEE division the reference performs.  No
+// shared-memory traffic at all -- in the bin kernel, which runs at the L1 data pipe's wavefront limit, the node
+// records are 40 % of the wavefronts.
+template <class T, int N, bool IS_ND, bool FIRST>
+__device__ __forceinline__ bool fast_weights_analytic(const Params<T>& P, const T (&p)[N], int (&k)[N], T (&t)[N]) {
+    constexpr bool kCollapse = IS_ND || (N == 1);
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        int kd = to_int_sat((p[d] - P.g0[d]) * P.inv_h[d]);
+        kd = max(0, min(kd, P.L[d] - 2));
+        const T G0 = P.g0[d] + (T)kd * P.h[d];
+        const T G1 = P.g0[d] + (T)(kd + 1) * P.h[d];
+        const T a = p[d] - G0;
+        const T w = G1 - G0;
+        // g[k] < p <= g[k+1] (strictly below where an exact hit collapses the axis); the hard-coded interpolators also
+        // take p == g[0] in the first cell under Clamp, where the reference computes t = 0 / w
+        const bool lower = (G0 < p[d]) || (FIRST && !kCollapse && kd == 0 && p[d] == G0);
+        const bool upper = kCollapse ? (p[d] < G1) : (p[d] <= G1);
+        ok = ok && lower && upper;
+        t[d] = a / w;
+        k[d] = kd;
+    }
+    return ok;
+}
+
 template <class T, int N, bool IS_ND, bool UNI, bool FIRST>
 __device__ __forceinline__ bool fast_weights(const Params<T>& P, const unsigned char* pack, const T (&p)[N], int (&k)[N],
                                              T (&t)[N]) {
@@ -142,7 +169,7 @@ __device__ __forceinline__ void ld_record(const unsigned char* src, float& t0, f
 // ---------------------------------------------------------------------------------------------
 // Bin: the point loop of interp_kernel with the gather replaced by an append to the point's list.
 // ---------------------------------------------------------------------------------------------
-template <class T, bool IS_ND, int PRE, bool UNI>
+template <class T, bool IS_ND, int PRE, bool UNI, bool ANA = false>
 __global__ void __launch_bounds__(kBlock, 4) tile_bin_kernel(const __grid_constant__ Params<T> P,
                                                               const __grid_constant__ TileGeom G) {
     constexpr int N = 3;
@@ -184,7 +211,9 @@ __global__ void __launch_bounds__(kBlock, 4) tile_bin_kernel(const __grid_consta
         }
         int k[N];
         T t[N];
-        if (fast_weights<T, N, IS_ND, UNI, PRE == kPreClamp>(P, pack, p, k, t)) {
+        const bool fast = ANA ? fast_weights_analytic<T, N, IS_ND, PRE == kPreClamp>(P, p, k, t)
+                              : fast_weights<T, N, IS_ND, UNI, PRE == kPreClamp>(P, pack, p, k, t);
+        if (fast) {
             const unsigned tile = (unsigned)(((k[0] >> G.sh[0]) * G.nt[1] + (k[1] >> G.sh[1])) * G.nt[2] + (k[2] >> G.sh[2]));
             const unsigned loc = (unsigned)(k[0] & ((1 << G.sh[0]) - 1)) | ((unsigned)(k[1] & ((1 << G.sh[1]) - 1)) << 8) |
                                  ((unsigned)(k[2] & ((1 << G.sh[2]) - 1)) << 16);
@@ -320,6 +349,7 @@ __device__ __forceinline__ void st_hint(float* p, float v, unsigned long long po
 template <class T>
 struct TileEval {
     T* out;
+    unsigned n;  // points of this launch (the last superchunk's window is shorter)
     const int* mode_flag;
     int mode_want;
 };
@@ -424,8 +454,24 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
     const int sx = G.box[1] * G.box[2];
     const unsigned long long keep_pol = (G.flags & 4u) ? make_table_policy(0.0f) : l2_policy_evict_last();
     unsigned tb = 0, tb_phase = 0, st = 0, st_phase = 0;
+    unsigned window_sc = ~0u;
     for (unsigned item = next_item(blockIdx.x); item < nitems; item = next_item(item + gridDim.x)) {
         const unsigned count = min(G.cursor[(size_t)item * kCursorStride], G.cap);
+        // On entering a superchunk, bring this CTA's share of its window of `out` into L2 (evict-last): an 8-byte
+        // store to a sector L2 does not hold is a write miss with a 32-byte fill from DRAM, one per point; after the
+        // coalesced prefetch the scattered stores of the whole superchunk are hits that merge into full lines.
+        const unsigned sc_now = item / (unsigned)G.ntiles;
+        if (sc_now != window_sc && !(G.flags & 16u)) {
+            window_sc = sc_now;
+            const size_t first = (size_t)sc_now << G.sc_shift;
+            const size_t last = min((size_t)E.n, first + ((size_t)1 << G.sc_shift));
+            const char* base = reinterpret_cast<const char*>(E.out + first);
+            const size_t lines = ((last - first) * sizeof(T) + 127) / 128;
+            const size_t per_cta = (lines + gridDim.x - 1) / gridDim.x;
+            const size_t lo = per_cta * blockIdx.x, hi = min(lines, lo + per_cta);
+            for (size_t l = lo + ct; l < hi; l += kEvalConsumers)
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + l * 128));
+        }
         mbar_wait(&tile_full[tb], tb_phase);
         const T* tile = reinterpret_cast<const T*>(tiles + (size_t)tb * G.buf_bytes);
         for (unsigned base = 0; base < count; base += kEvalChunk) {
@@ -539,7 +585,7 @@ __global__ void __launch_bounds__(kProbeThreads) order_probe2_kernel(const __gri
 
 // Launch interface (nint_tile_f64.cu).
 struct TileLaunch {
-    int is_nd, all_uniform, sm_count;
+    int is_nd, all_uniform, all_analytic, sm_count;
     unsigned smem_bytes;  // axis pack staged by the bin kernel
     void* stream;
 };

@@ -9,9 +9,9 @@ extern std::atomic<unsigned long long> g_launch_count;
 
 namespace {
 
-template <class T, bool IS_ND, int PRE, bool UNI>
+template <class T, bool IS_ND, int PRE, bool UNI, bool ANA = false>
 cudaError_t launch_bin_variant(const Params<T>& P, const TileGeom& G, const TileLaunch& cfg) {
-    auto kern = tile_bin_kernel<T, IS_ND, PRE, UNI>;
+    auto kern = tile_bin_kernel<T, IS_ND, PRE, UNI, ANA>;
     const unsigned smem = cfg.smem_bytes;
     if (smem > 40u * 1024u) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -38,6 +38,7 @@ cudaError_t launch_bin_variant(const Params<T>& P, const TileGeom& G, const Tile
 
 template <class T, bool IS_ND, int PRE>
 cudaError_t launch_bin_uni(const Params<T>& P, const TileGeom& G, const TileLaunch& cfg) {
+    if (cfg.all_uniform && cfg.all_analytic) return launch_bin_variant<T, IS_ND, PRE, true, true>(P, G, cfg);
     return cfg.all_uniform ? launch_bin_variant<T, IS_ND, PRE, true>(P, G, cfg) : launch_bin_variant<T, IS_ND, PRE, false>(P, G, cfg);
 }
 template <class T, bool IS_ND>

@@ -21,6 +21,8 @@ def _axes(rng, lens, dtype, mode="nonuniform"):
     for L in lens:
         if mode == "uniform":
             g = (np.arange(L) * 0.37 - 1.3).astype(dtype)
+        elif mode == "analytic":  # nodes are exactly k * h in `dtype`: the bin kernel computes them instead of loading them
+            g = np.arange(L, dtype=dtype) * dtype(0.37)
         elif mode == "log":
             g = np.sort(np.unique(np.logspace(-6, 3, L).astype(dtype)))
             if len(g) < L:
@@ -332,7 +334,9 @@ def test_binned_tile_route(monkeypatch):
                                                          (FIXED, (37, 35, 70), np.float64, "nonuniform", 15, 17),
                                                          (ND, (21, 40, 36), np.float32, "nonuniform", 17, 28),
                                                          (ND, (50, 18, 34), np.float64, "uniform", 23, 28),
-                                                         (FIXED, (18, 67, 72), np.float32, "uniform", 14, 16)]:
+                                                         (FIXED, (18, 67, 72), np.float32, "uniform", 14, 16),
+                                                         (FIXED, (45, 33, 66), np.float64, "analytic", 15, 17),
+                                                         (ND, (20, 35, 40), np.float32, "analytic", 16, 28)]:
         monkeypatch.setenv("NINT_TILE_SC_SHIFT", str(sc_shift))
         monkeypatch.setenv("NINT_TILE_SEG_SHIFT", str(seg_shift))
         # distinct cells per window of 4096 consecutive points: ~4000 (or every cell) in random order, the cells of a
