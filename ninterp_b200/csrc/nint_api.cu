@@ -590,7 +590,12 @@ bool tile_route(const nint_handle* h, size_t n, int windows) {
     const char* route = std::getenv("NINT_ROUTE");
     const char* e_on = std::getenv("NINT_SLABS");
     if (route && (!std::strcmp(route, "slab") || !std::strcmp(route, "single"))) return false;
-    if (e_on && !(route && !std::strcmp(route, "tile"))) return false;  // NINT_SLABS=k pins the older routes
+    const bool forced = route && !std::strcmp(route, "tile");
+    if (e_on && !forced) return false;  // NINT_SLABS=k pins the older routes
+    // Measured on B200 (256^3, 1e9 random points): slab passes 31.6 ms (f64) / 19.6 ms (f32), binned tiles 35.9 / 30.3 ms,
+    // single pass 50.6 ms.  So the slab passes keep the batches they can take, and the binned tiles take the ones
+    // they cannot: Extrapolate::Wrap, which re-maps coordinates across axes.
+    if (windows > 0 && !forced) return false;
     for (int d = 0; d < 3; ++d)
         if (!(h->ax[d].flags & nint::kAxisFast)) return false;
     const char* e_bytes = std::getenv("NINT_SLAB_MIN_BYTES");
@@ -604,8 +609,7 @@ bool tile_route(const nint_handle* h, size_t n, int windows) {
     // every superchunk streams the table once: beyond ~40 bytes per point of that the slab passes or the single
     // pass are the better deal
     const double per_point = plain * 1.2 / (double)(1ull << h->tile_geom.sc_shift);
-    if (!(route && !std::strcmp(route, "tile")) && per_point > 48.0) return false;
-    (void)windows;
+    if (!forced && per_point > 48.0) return false;
     return true;
 }
 
@@ -639,7 +643,7 @@ void build_tile(nint_handle* h) {
     g.ntiles = (int)ntiles;
     g.tile_bytes = (unsigned)(vol * es);
     g.buf_bytes = (g.tile_bytes + 127u) & ~127u;
-    unsigned sc_shift = 23;
+    unsigned sc_shift = 22;  // 4 Mi points: a 32 MB window of f64 results stays in L2; 2^23 measured 30 % slower
     if (const char* env = std::getenv("NINT_TILE_SC_SHIFT")) sc_shift = (unsigned)std::atoi(env);
     g.sc_shift = std::min(28u, std::max(10u, sc_shift));
     const unsigned long long per_list = (1ull << g.sc_shift) / ntiles;
@@ -816,8 +820,10 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     if (e != cudaSuccess) return cuda_fail(e, "order probe launch");
     P.mode_flag = flag;
     P.mode_want = nint::kModeCoherent;
+    P.blocked = std::getenv("NINT_NO_BLOCKED") ? 0 : 1;
     e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : nint::launch_fixed<T>(P, cfg);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    P.blocked = 0;
     P.mode_want = nint::kModeRandom;
     if (tile) {
         const int rc = launch_tiles<T>(h, P, cfg, stream);

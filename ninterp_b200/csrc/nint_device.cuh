@@ -69,6 +69,7 @@ struct Params {
     // lies in (win_lo_x, win_hi_x]; the first window is open below (and takes NaN), the last is open above.
     const int* mode_flag;
     int mode_want;
+    int blocked;  // interp_kernel: every CTA walks one contiguous range of the batch instead of striding over it
     T win_lo_x, win_hi_x;
     int win_first, win_last;
     int L[kMaxDim];
@@ -736,9 +737,19 @@ __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_ke
     if (threadIdx.x < 4) s_info[threadIdx.x] = (threadIdx.x < 2) ? 0ull : ~0ull;
     __syncthreads();
 
-    const unsigned n = (unsigned)P.n;  // <= 2^30, so i + stride cannot wrap
-    const unsigned stride = gridDim.x * blockDim.x;
+    // Grid-stride over the batch, or -- for batches the order probe found coherent -- one contiguous range per CTA:
+    // consecutive queries then share cells inside one SM's L1 instead of being dealt out to all SMs (queries grouped
+    // by 8^3-cell tiles: 81 -> see DESIGN.md).  `n` is the end of this CTA's range; <= 2^30, so i + stride cannot wrap.
+    unsigned n = (unsigned)P.n;
+    unsigned stride = gridDim.x * blockDim.x;
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P.blocked) {
+        const unsigned chunk = ((n + gridDim.x - 1) / gridDim.x + kBlock - 1) / kBlock * kBlock;
+        const unsigned long long lo = (unsigned long long)blockIdx.x * chunk;
+        i = (unsigned)min(lo, (unsigned long long)n) + threadIdx.x;
+        n = (unsigned)min(lo + chunk, (unsigned long long)n);
+        stride = blockDim.x;
+    }
     Point<T, N> q;
     if (i < n) {
 #pragma unroll

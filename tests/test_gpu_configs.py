@@ -65,13 +65,32 @@ def test_config3_interp3d_linear_256cubed():
         assert_same(got, st, want, st_want, "random order")
         assert info == expected_info(st_want) and (st == 0).all()
         assert _lib.lib().nint_last_query_order(g._h) == 2  # incoherent ...
-        assert _lib.lib().nint_last_incoherent_route(g._h) == 2  # ... binned tiles staged by TMA
+        assert _lib.lib().nint_last_incoherent_route(g._h) == 1  # ... slab passes over the plain table
         # cell-sorted order must give the same values as the unsorted batch, through the single pass
         order = np.lexsort([np.searchsorted(axes[2], cols[2]), np.searchsorted(axes[1], cols[1]),
                             np.searchsorted(axes[0], cols[0])])
         got, st, info = gpu_eval(g, [c[order] for c in cols])
         assert_same(got, st, want[order], st_want[order], "cell order")
         assert _lib.lib().nint_last_query_order(g._h) == 1
+
+
+def test_config3_wrap_takes_the_binned_tiles():
+    # the same table under Extrapolate::Wrap (coordinates are re-mapped across axes, so the slab passes do not apply):
+    # incoherent batches are bucketed by grid tile and evaluated from TMA-staged tiles in shared memory
+    from gpu_util import assert_same, expected_info, gpu_eval, make_pair
+
+    from ninterp_b200 import _lib
+
+    rng = np.random.default_rng(33)
+    v = rng.uniform(0, 1, (256, 256, 256))
+    axes = [np.arange(256) * (1.0 / 255)] * 3
+    cols = [rng.uniform(-0.3, 1.3, 6_000_000) for _ in axes]
+    g, o = make_pair(0, axes, v, LIN, WRAP, dtype=np.float64)
+    want, st_want = o.eval(cols, nthreads=O.max_threads())
+    got, st, info = gpu_eval(g, cols)
+    assert_same(got, st, want, st_want, "wrap, random order")
+    assert info == expected_info(st_want)
+    assert _lib.lib().nint_last_query_order(g._h) == 2 and _lib.lib().nint_last_incoherent_route(g._h) == 2
 
 
 def test_config4_interpnd_f32_n5_wrap_fill():

@@ -31,7 +31,7 @@ def main():
     n = int(a.points)
     dev = torch.device("cuda", 0)
     rng = np.random.default_rng(0)
-    if a.case in ("random", "sorted", "nonuniform"):
+    if a.case in ("random", "sorted", "nonuniform", "tilesorted", "morton"):
         axes, values = bench.grid_and_values(uniform=a.case != "nonuniform", GRID=a.grid)
         strat = nb.strategy.Nearest if a.strategy == "nearest" else nb.strategy.Linear
         npdt = np.float32 if a.dtype == "f32" else np.float64
@@ -39,6 +39,10 @@ def main():
         cols = bench.gen_random(torch, n, dev, seed=1)
         if a.case == "sorted":
             bench.fill_cell_sorted(torch, cols, dev, seed=2, GRID=a.grid)
+        elif a.case == "tilesorted":
+            bench.fill_tile_sorted(torch, cols, dev, seed=2, GRID=a.grid)
+        elif a.case == "morton":
+            bench.fill_morton(torch, cols, dev, seed=2, GRID=a.grid)
         tdt = torch.float32 if a.dtype == "f32" else torch.float64
         if a.dtype == "f32":
             cols = [c.to(torch.float32).clamp_(0.0, 1.0) for c in cols]
