@@ -796,6 +796,15 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     cfg.all_uniform = 1;
     for (int d = 0; d < h->ndim_eff; ++d)
         if ((h->ax[d].flags & (nint::kAxisUniform | nint::kAxisFast)) != (nint::kAxisUniform | nint::kAxisFast)) cfg.all_uniform = 0;
+    // NINT_ANALYTIC=1: coherent single pass with computed nodes (measured: see DESIGN.md); the bin kernel always uses them
+    cfg.all_analytic = 0;
+    if (const char* env = std::getenv("NINT_ANALYTIC")) {
+        if (std::atoi(env)) {
+            cfg.all_analytic = 1;
+            for (int d = 0; d < h->ndim_eff; ++d)
+                if (!(h->ax[d].flags & nint::kAxisAnalytic)) cfg.all_analytic = 0;
+        }
+    }
     cfg.smem_bytes = h->pack_hot_bytes;
     cfg.sm_count = h->sm_count;
     cfg.stream = stream;

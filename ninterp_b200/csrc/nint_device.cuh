@@ -596,13 +596,60 @@ __device__ __forceinline__ bool verify_retry(const AxisRef<T>& ax, T p, int& k, 
     return ok;
 }
 
+// Cell guess, verification and weights for axes whose nodes are exactly g0 + k * h (checked bit for bit on the host,
+// Params::h): the two nodes of the guessed cell are computed instead of loaded, and t = a / w is the IEEE division the
+// reference performs.  No shared-memory traffic at all: where the L1 data pipe is the limit (queries that are random
+// inside a small region: one wavefront per lane and load) the node records are 40 % of the wavefronts.
+template <class T, int N, bool IS_ND, bool FIRST>
+__device__ __forceinline__ bool fast_weights_analytic(const Params<T>& P, const T (&p)[N], int (&k)[N], T (&t)[N]) {
+    constexpr bool kCollapse = IS_ND || (N == 1);
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        int kd = to_int_sat((p[d] - P.g0[d]) * P.inv_h[d]);
+        kd = max(0, min(kd, P.L[d] - 2));
+        const T G0 = P.g0[d] + (T)kd * P.h[d];
+        const T G1 = P.g0[d] + (T)(kd + 1) * P.h[d];
+        const T a = p[d] - G0;
+        const T w = G1 - G0;
+        // g[k] < p <= g[k+1] (strictly below where an exact hit collapses the axis); the hard-coded interpolators also
+        // take p == g[0] in the first cell under Clamp, where the reference computes t = 0 / w
+        const bool lower = (G0 < p[d]) || (FIRST && !kCollapse && kd == 0 && p[d] == G0);
+        const bool upper = kCollapse ? (p[d] < G1) : (p[d] <= G1);
+        ok = ok && lower && upper;
+        t[d] = a / w;
+        k[d] = kd;
+    }
+    return ok;
+}
+
 // The whole fast path for one point; false when anything about it needs the general path.
-template <class T, int N, bool IS_ND, int STRAT, bool UNI, bool FIRST, bool PLAIN = false>
+template <class T, int N, bool IS_ND, int STRAT, bool UNI, bool FIRST, bool PLAIN = false, bool ANA = false>
 __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned char* pack, unsigned long long pol,
                                            const T (&p)[N], T& result) {
     constexpr bool kCollapse = IS_ND || (N == 1);
     int k[N];
     bool ok = true;
+    if (ANA && STRAT == NINT_LINEAR) {
+        T t[N];
+        ok = fast_weights_analytic<T, N, IS_ND, FIRST>(P, p, k, t);
+        if (N >= 4 && !ok) return false;
+        T cube[1 << N];
+        unsigned cell = 0;  // the analytic kernels are only dispatched when the cell-packed table exists
+#pragma unroll
+        for (int d = 0; d < N; ++d) cell += (unsigned)k[d] * (unsigned)P.cstride[d];
+        ld_cells<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            const int half = 1 << (N - 1 - d);
+            const T td = t[d];
+            const T sd = T(1) - td;
+#pragma unroll
+            for (int j = 0; j < half; ++j) cube[j] = cube[j] * sd + cube[half + j] * td;
+        }
+        result = cube[0];
+        return ok;
+    }
 #pragma unroll
     for (int d = 0; d < N; ++d) {
         const unsigned* guess = UNI ? nullptr : reinterpret_cast<const unsigned*>(pack + P.guess_off[d]);
@@ -717,7 +764,7 @@ constexpr int min_ctas(int n, int elem_bytes) {
     return (n == 4 || (n == 5 && elem_bytes == 4)) ? 2 : 1;
 }
 
-template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE, bool UNI>
+template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE, bool UNI, bool ANA = false>
 __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_kernel(const __grid_constant__ Params<T> P) {
     extern __shared__ __align__(16) unsigned char smem_pack[];
     if (P.mode_flag != nullptr && *P.mode_flag != P.mode_want) return;  // the other query-order mode runs this batch
@@ -775,7 +822,7 @@ __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_ke
             }
         }
         T result;
-        const bool ok = fast_point<T, N, IS_ND, STRAT, UNI, PRE == kPreClamp>(P, pack, pol, p, result);
+        const bool ok = fast_point<T, N, IS_ND, STRAT, UNI, PRE == kPreClamp, false, ANA>(P, pack, pol, p, result);
         // 3-D f64 is the kernel that lives at the edge of its 64 registers: there the common case stores on its
         // own, so that no status or result register is shared with the slow path (cell-ordered queries 152 -> 157
         // Gpoints/s).  The other kernels measured faster with the single store after the join (2-D: 84 vs 72).
@@ -1033,6 +1080,7 @@ struct LaunchCfg {
     int strategy;
     int smem_axes;  // stage the axis pack in shared memory
     int all_uniform;  // every axis is uniform and fast-path eligible
+    int all_analytic; // ... and its nodes are exactly g0 + k * h (launch the kernels that compute them)
     int slab;         // launch slab_kernel (Params::win_*) instead of interp_kernel
     unsigned smem_bytes;
     int sm_count;

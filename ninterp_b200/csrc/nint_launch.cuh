@@ -8,9 +8,9 @@ namespace nint {
 
 extern std::atomic<unsigned long long> g_launch_count;
 
-template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE, bool UNI>
+template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE, bool UNI, bool ANA = false>
 cudaError_t launch_variant(const Params<T>& P, const LaunchCfg& cfg) {
-    auto kern = interp_kernel<T, N, IS_ND, STRAT, SMEM, PRE, UNI>;
+    auto kern = interp_kernel<T, N, IS_ND, STRAT, SMEM, PRE, UNI, ANA>;
     const unsigned smem = SMEM ? cfg.smem_bytes : 0u;
     if (smem > 48u * 1024u) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -41,6 +41,10 @@ cudaError_t launch_variant(const Params<T>& P, const LaunchCfg& cfg) {
 // their axis pack lives.
 template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE>
 cudaError_t launch_uni(const Params<T>& P, const LaunchCfg& cfg) {
+    // analytic axes: only the hard-coded 2-D/3-D Linear interpolators with axes in shared memory get the extra kernels
+    if constexpr (STRAT == NINT_LINEAR && SMEM && !IS_ND && (N == 2 || N == 3)) {
+        if (cfg.all_uniform && cfg.all_analytic && P.cells != nullptr) return launch_variant<T, N, IS_ND, STRAT, SMEM, PRE, true, true>(P, cfg);
+    }
     if (cfg.all_uniform && (STRAT != NINT_LINEAR || P.cells != nullptr))
         return launch_variant<T, N, IS_ND, STRAT, SMEM, PRE, true>(P, cfg);
     return launch_variant<T, N, IS_ND, STRAT, SMEM, PRE, false>(P, cfg);

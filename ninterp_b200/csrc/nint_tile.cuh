@@ -57,33 +57,6 @@ __device__ __forceinline__ size_t record_offset(const TileGeom& G, unsigned sc, 
 
 // First half of fast_point() for Linear: cell guess, verification and weights of every axis.  Same functions, same
 // order, so a point is accepted here exactly when the single pass accepts it, with the same k and t.
-// The same for axes whose nodes are exactly g0 + k * h (checked bit for bit on the host, Params::h): the two nodes of
-// the guessed cell are computed instead of loaded, and t = a / w is the IEEE division the reference performs.  No
-// shared-memory traffic at all -- in the bin kernel, which runs at the L1 data pipe's wavefront limit, the node
-// records are 40 % of the wavefronts.
-template <class T, int N, bool IS_ND, bool FIRST>
-__device__ __forceinline__ bool fast_weights_analytic(const Params<T>& P, const T (&p)[N], int (&k)[N], T (&t)[N]) {
-    constexpr bool kCollapse = IS_ND || (N == 1);
-    bool ok = true;
-#pragma unroll
-    for (int d = 0; d < N; ++d) {
-        int kd = to_int_sat((p[d] - P.g0[d]) * P.inv_h[d]);
-        kd = max(0, min(kd, P.L[d] - 2));
-        const T G0 = P.g0[d] + (T)kd * P.h[d];
-        const T G1 = P.g0[d] + (T)(kd + 1) * P.h[d];
-        const T a = p[d] - G0;
-        const T w = G1 - G0;
-        // g[k] < p <= g[k+1] (strictly below where an exact hit collapses the axis); the hard-coded interpolators also
-        // take p == g[0] in the first cell under Clamp, where the reference computes t = 0 / w
-        const bool lower = (G0 < p[d]) || (FIRST && !kCollapse && kd == 0 && p[d] == G0);
-        const bool upper = kCollapse ? (p[d] < G1) : (p[d] <= G1);
-        ok = ok && lower && upper;
-        t[d] = a / w;
-        k[d] = kd;
-    }
-    return ok;
-}
-
 template <class T, int N, bool IS_ND, bool UNI, bool FIRST>
 __device__ __forceinline__ bool fast_weights(const Params<T>& P, const unsigned char* pack, const T (&p)[N], int (&k)[N],
                                              T (&t)[N]) {

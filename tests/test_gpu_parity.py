@@ -316,6 +316,26 @@ def test_slab_passes_and_order_probe(monkeypatch):
     assert _lib.lib().nint_last_query_order(g._h) == 0
 
 
+def test_analytic_uniform_axes(monkeypatch):
+    # axes whose nodes are exactly k * h (arange * h) may have their nodes computed instead of loaded, with IEEE division
+    # for the weights (NINT_ANALYTIC=1 on the single pass; the bin kernel of the tile route always does): same bits
+    from gpu_util import assert_same, expected_info, gpu_eval, make_pair
+
+    monkeypatch.setenv("NINT_ANALYTIC", "1")
+    rng = np.random.default_rng(515)
+    for kind, lens, dtype in [(FIXED, (40, 33, 26), np.float64), (FIXED, (57, 31), np.float64), (FIXED, (19, 22, 35), np.float32),
+                              (FIXED, (64, 48), np.float32)]:
+        axes = _axes(rng, lens, dtype, "analytic")
+        values = rng.uniform(-1, 1, lens).astype(dtype)
+        cols = _queries(rng, axes, 200_000, dtype, 0.1)
+        for extrap in (ERROR, CLAMP, ENABLE, FILL, WRAP):
+            g, o = make_pair(kind, axes, values, LIN, extrap, fill=0.5, dtype=dtype)
+            got, st, info = gpu_eval(g, cols)
+            want, st_want = o.eval(cols, nthreads=O.max_threads())
+            assert_same(got, st, want, st_want, f"analytic {lens} {dtype.__name__} {extrap}")
+            assert info == expected_info(st_want)
+
+
 def test_binned_tile_route(monkeypatch):
     # Incoherent batches on 3-D Linear tables beyond L2 are bucketed by grid tile and evaluated from TMA-staged tiles
     # in shared memory (nint_tile.cuh).  Forced here on small tables, with small superchunks and segments so that a
