@@ -125,6 +125,8 @@ struct nint_handle {
     void* d_values = nullptr;
     void* d_cells = nullptr;  // cell-packed copy of the table for Linear (2^N corners per cell), or NULL
     unsigned char* d_pack = nullptr;
+    unsigned char* d_fused = nullptr;  // 1-D Linear: {node, value} pairs, reciprocals and guess table for shared memory
+    unsigned fused_bytes = 0, fused_rcp_off = 0, fused_guess_off = 0;
     unsigned pack_bytes = 0;      // whole pack in global memory
     unsigned pack_hot_bytes = 0;  // leading part the kernels stage in shared memory: records and guess tables
     bool smem_axes = true;
@@ -432,6 +434,52 @@ int build_pack(nint_handle* h) {
     return NINT_OK;
 }
 
+// 1-D interpolators: the fused pack of interp1d_fused_kernel.  Built when the axis can use the fast path and the pack
+// fits four resident CTAs' shared memory; NINT_FUSED_1D=0 disables it.
+int build_fused1d(nint_handle* h) {
+    if (h->constant || h->ndim_eff != 1 || !(h->ax[0].flags & nint::kAxisFast)) return NINT_OK;
+    if (const char* env = std::getenv("NINT_FUSED_1D"))
+        if (std::atoi(env) == 0) return NINT_OK;
+    const size_t es = elem_size(h->dtype);
+    const AxisMeta& a = h->ax[0];
+    const size_t L = (size_t)a.L;
+    const bool uniform = (a.flags & nint::kAxisUniform) != 0;
+    const size_t pairs_bytes = (size_t)align_up((L + 1) * 2 * es, 16);
+    const size_t rcp_bytes = (size_t)align_up(L * es, 16);
+    const size_t guess_bytes = uniform ? 0 : (size_t)align_up((unsigned long long)a.M * 4, 16);
+    const size_t total = pairs_bytes + rcp_bytes + guess_bytes;
+    if (total > 56u * 1024u) return NINT_OK;
+    std::vector<unsigned char> buf(total, 0);
+    const unsigned char* nodes = h->axes_host[0].data();
+    std::vector<unsigned char> vals_host(L * es);  // the dense device copy (strided views were gathered at upload)
+    NINT_CUDA(cudaMemcpy(vals_host.data(), h->d_values, L * es, cudaMemcpyDeviceToHost));
+    const unsigned char* vals = vals_host.data();
+    for (size_t l = 0; l <= L; ++l) {
+        unsigned char* rec = buf.data() + l * 2 * es;
+        if (l < L) {
+            std::memcpy(rec, nodes + l * es, es);
+            std::memcpy(rec + es, vals + l * es, es);
+        } else if (h->dtype == NINT_F64) {
+            const double inf = std::numeric_limits<double>::infinity();
+            std::memcpy(rec, &inf, es);
+        } else {
+            const float inf = std::numeric_limits<float>::infinity();
+            std::memcpy(rec, &inf, es);
+        }
+    }
+    // reciprocals and guess table: copies of what build_pack() prepared (same bits as the general kernel uses)
+    std::vector<unsigned char> pack(h->pack_bytes);
+    NINT_CUDA(cudaMemcpy(pack.data(), h->d_pack, h->pack_bytes, cudaMemcpyDeviceToHost));
+    for (size_t l = 0; l < L; ++l) std::memcpy(buf.data() + pairs_bytes + l * es, pack.data() + a.node_off + (l * 2 + 1) * es, es);
+    if (!uniform) std::memcpy(buf.data() + pairs_bytes + rcp_bytes, pack.data() + a.guess_off, (size_t)a.M * 4);
+    NINT_CUDA(cudaMalloc((void**)&h->d_fused, total));
+    NINT_CUDA(cudaMemcpy(h->d_fused, buf.data(), total, cudaMemcpyHostToDevice));
+    h->fused_bytes = (unsigned)total;
+    h->fused_rcp_off = (unsigned)pairs_bytes;
+    h->fused_guess_off = (unsigned)(pairs_bytes + rcp_bytes);
+    return NINT_OK;
+}
+
 // ------------------------------------------------------------------------------- value table
 int upload_values(nint_handle* h, const void* values_host, const ptrdiff_t* strides) {
     const size_t es = elem_size(h->dtype);
@@ -531,6 +579,10 @@ void fill_params(const nint_handle* h, nint::Params<T>& P) {
     P.fill = (T)h->fill;
     P.extrap = h->extrap;
     P.l2_frac = h->l2_frac;
+    P.fused = h->d_fused;
+    P.fused_bytes = h->fused_bytes;
+    P.fused_rcp_off = h->fused_rcp_off;
+    P.fused_guess_off = h->fused_guess_off;
     for (int d = 0; d < h->ndim_eff; ++d) {
         const AxisMeta& a = h->ax[d];
         P.L[d] = a.L;
@@ -805,6 +857,14 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
                 if (!(h->ax[d].flags & nint::kAxisAnalytic)) cfg.all_analytic = 0;
         }
     }
+    cfg.slab_analytic = 0;
+    if (const char* env = std::getenv("NINT_SLAB_ANALYTIC")) {
+        if (std::atoi(env)) {
+            cfg.slab_analytic = 1;
+            for (int d = 0; d < h->ndim_eff; ++d)
+                if (!(h->ax[d].flags & nint::kAxisAnalytic)) cfg.slab_analytic = 0;
+        }
+    }
     cfg.smem_bytes = h->pack_hot_bytes;
     cfg.sm_count = h->sm_count;
     cfg.stream = stream;
@@ -1061,6 +1121,7 @@ int nint_create(int device, int kind, int dtype, int ngrid, const size_t* axis_l
     }
     rc = upload_values(h, values_host, value_strides);
     if (rc == NINT_OK && !h->constant) rc = build_pack(h);
+    if (rc == NINT_OK) rc = build_fused1d(h);
     if (rc == NINT_OK) rc = build_cells(h);
     if (rc == NINT_OK) {
         build_tile(h);
@@ -1088,6 +1149,7 @@ void nint_destroy(nint_handle* h) {
         if (h->d_values) cudaFree(h->d_values);
         if (h->d_cells) cudaFree(h->d_cells);
         if (h->d_pack) cudaFree(h->d_pack);
+        if (h->d_fused) cudaFree(h->d_fused);
         if (h->d_info) cudaFree(h->d_info);
         if (h->d_probe) cudaFree(h->d_probe);
         if (h->pool) cudaMemPoolDestroy(h->pool);

@@ -84,6 +84,9 @@ struct Params {
     T inv_w[kMaxDim];            // buckets per unit length (guess table and {lo, hi} table share the buckets)
     T inv_h[kMaxDim];            // cells per unit length (uniform axes)
     T h[kMaxDim];                // cell width of an analytic axis (kAxisAnalytic): g[k] == g0 + k * h exactly
+    // Interp1D / 1-D InterpND Linear: fused pack {node, value} pairs + cell reciprocals (+ guess table), or NULL
+    const unsigned char* fused;
+    unsigned fused_bytes, fused_rcp_off, fused_guess_off;
 };
 
 template <class T>
@@ -635,10 +638,21 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
         ok = fast_weights_analytic<T, N, IS_ND, FIRST>(P, p, k, t);
         if (N >= 4 && !ok) return false;
         T cube[1 << N];
-        unsigned cell = 0;  // the analytic kernels are only dispatched when the cell-packed table exists
+        if (!PLAIN) {
+            unsigned cell = 0;  // the analytic single-pass kernels are only dispatched when the cell-packed table exists
 #pragma unroll
-        for (int d = 0; d < N; ++d) cell += (unsigned)k[d] * (unsigned)P.cstride[d];
-        ld_cells<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
+            for (int d = 0; d < N; ++d) cell += (unsigned)k[d] * (unsigned)P.cstride[d];
+            ld_cells<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
+        } else {
+            long long base = 0;
+            long long step[N];
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                base += (long long)k[d] * P.vstride[d];
+                step[d] = P.vstride[d];
+            }
+            gather_rows<T, N>(P.values + base, step, pol, false, cube);
+        }
 #pragma unroll
         for (int d = 0; d < N; ++d) {
             const int half = 1 << (N - 1 - d);
@@ -902,6 +916,114 @@ __global__ void __launch_bounds__(kBlock, min_ctas(N, (int)sizeof(T))) interp_ke
 }
 
 // ---------------------------------------------------------------------------------------------
+// 1-D Linear with everything a point needs in shared memory (one/strategies.rs:9-29).
+//
+// The general kernel reads, per point, a guess-table entry, the node record {g[k], 1/w}, the next node and the value
+// pair v[k], v[k+1] -- the last from global memory, where 32 lanes in 32 random cells are 32 L1 wavefronts; on a
+// 1000-node axis the L1 data pipe ran at 97 % of its wavefront rate (202 Gpoints/s, half the HBM roofline).  Here the
+// axis and the values are interleaved as {g[l], v[l]} pairs, staged once per CTA with the reciprocals, so a point is
+// two 16-byte and one 8-byte shared-memory loads after the guess.  Same verification (g[k] < p < g[k+1], exact hits
+// leave for the general path, which selects the node value) and the same arithmetic as fast_point<N = 1>.
+// ---------------------------------------------------------------------------------------------
+template <class T, bool IS_ND, int PRE, bool UNI>
+__global__ void __launch_bounds__(kBlock, 4) interp1d_fused_kernel(const __grid_constant__ Params<T> P) {
+    constexpr int N = 1;
+    extern __shared__ __align__(16) unsigned char smem_pack[];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(P.fused);
+        uint4* dst = reinterpret_cast<uint4*>(smem_pack);
+        for (unsigned i = threadIdx.x; i < P.fused_bytes / 16u; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    const T* pairs = reinterpret_cast<const T*>(smem_pack);                      // {g[l], v[l]}, l = 0..L (last: +inf pad)
+    const T* rcps = reinterpret_cast<const T*>(smem_pack + P.fused_rcp_off);     // RN(1 / (g[l+1] - g[l]))
+    const unsigned* guess = reinterpret_cast<const unsigned*>(smem_pack + P.fused_guess_off);
+    __shared__ unsigned long long s_info[4];  // n_error, n_panic, first_error, first_panic
+    if (threadIdx.x < 4) s_info[threadIdx.x] = (threadIdx.x < 2) ? 0ull : ~0ull;
+    __syncthreads();
+    const unsigned n = (unsigned)P.n;
+    const unsigned stride = gridDim.x * blockDim.x;
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int L = P.L[0];
+    const T g0 = P.g0[0], gl = P.gl[0];
+    T q = T(0), q2 = T(0);
+    if (i < n) q = ld_stream(P.coords[0] + (size_t)i * P.coord_stride);
+    auto process = [&](unsigned i, T q) {
+        T p = (PRE == kPreClamp) ? clamp_coord(q, g0, gl) : q;
+        if (PRE == kPreWrap) {
+            if (!(g0 <= q && q <= gl)) p = wrap_coord(q, g0, gl);  // lib.rs:81-83 on the single axis (one/mod.rs:189-196)
+        }
+        int k;
+        if (UNI) {
+            k = to_int_sat((p - g0) * P.inv_h[0]);
+        } else {
+            int b = to_int_sat((p - g0) * P.inv_w[0]);
+            b = max(0, min(b, P.M[0] - 1));
+            k = (int)guess[b];
+        }
+        k = max(0, min(k, L - 2));
+        T G0, V0, G1, V1, r;
+        ld_rec(pairs + 2 * k, G0, V0);
+        ld_rec(pairs + 2 * k + 2, G1, V1);
+        r = rcps[k];
+        T a = p - G0;
+        bool ok = (p < G1) && in_div_window_pos(a);
+        if (!UNI) {
+            if (!ok && k < L - 2 && p > G1) {  // the bucket's left edge was in the previous cell: once more with the next
+                ++k;
+                G0 = G1;
+                V0 = V1;
+                ld_rec(pairs + 2 * k + 2, G1, V1);
+                r = rcps[k];
+                a = p - G0;
+                ok = (p < G1) && in_div_window_pos(a);
+            }
+        }
+        unsigned status = NINT_STATUS_OK;
+        T result;
+        if (ok) {
+            const T t = div_markstein<T>(a, G1 - G0, r);
+            result = V0 * (T(1) - t) + V1 * t;  // one/strategies.rs:28
+        } else {
+            Point<T, N> qq;
+            qq.v[0] = q;
+            const Outcome<T> o = general_point<T, N, IS_ND, NINT_LINEAR>(P, P.pack, qq);  // axis pack from global memory
+            result = o.value;
+            status = o.status;
+            if (status != NINT_STATUS_OK) {
+                result = quiet_nan<T>();
+                const int slot = (status == NINT_STATUS_PANIC) ? 1 : 0;
+                atomicAdd(&s_info[slot], 1ull);
+                atomicMin(&s_info[2 + slot], (unsigned long long)i + P.index_base);
+            }
+        }
+        st_stream(P.out + i, result);
+        if (P.status) P.status[i] = (uint8_t)status;
+    };
+    while (i < n) {
+        const unsigned in = i + stride;
+        const bool more = in < n;
+        if (more) q2 = ld_stream(P.coords[0] + (size_t)in * P.coord_stride);
+        process(i, q);
+        if (!more) break;
+        i = in;
+        q = q2;
+    }
+    if (P.info) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (s_info[0]) {
+                atomicAdd((unsigned long long*)&P.info->n_error, s_info[0]);
+                atomicMin((unsigned long long*)&P.info->first_error, s_info[2]);
+            }
+            if (s_info[1]) {
+                atomicAdd((unsigned long long*)&P.info->n_panic, s_info[1]);
+                atomicMin((unsigned long long*)&P.info->first_panic, s_info[3]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Slab passes for incoherent queries on tables larger than L2 (Linear).
 //
 // When consecutive queries land in unrelated cells and the table does not fit L2, every corner load is a DRAM
@@ -922,7 +1044,7 @@ constexpr unsigned kSlabSpan = 32u * kSlabPer;  // points a warp scans at a time
 // headline workload; at 80 registers (3 CTAs, no spills) 32.7; at 96 (2 CTAs) 31.4; at 48 (5 CTAs) 25.6.
 constexpr int slab_ctas(int n, int elem_bytes) { return n <= 3 ? 3 : min_ctas(n, elem_bytes); }
 
-template <class T, int N, bool IS_ND, int PRE, bool UNI>
+template <class T, int N, bool IS_ND, int PRE, bool UNI, bool ANA = false>
 __global__ void __launch_bounds__(kBlock, slab_ctas(N, (int)sizeof(T))) slab_kernel(const __grid_constant__ Params<T> P) {
     extern __shared__ __align__(16) unsigned char smem_pack[];
     __shared__ unsigned short s_list[kBlock / 32][kSlabSpan];
@@ -956,7 +1078,7 @@ __global__ void __launch_bounds__(kBlock, slab_ctas(N, (int)sizeof(T))) slab_ker
         for (int d = 0; d < N; ++d) p[d] = (PRE == kPreClamp) ? clamp_coord(q.v[d], P.g0[d], P.gl[d]) : q.v[d];
         unsigned status = NINT_STATUS_OK;
         T result;
-        const bool ok = fast_point<T, N, IS_ND, NINT_LINEAR, UNI, PRE == kPreClamp, true>(P, pack, pol, p, result);
+        const bool ok = fast_point<T, N, IS_ND, NINT_LINEAR, UNI, PRE == kPreClamp, true, ANA>(P, pack, pol, p, result);
         if (!ok) {
             const Outcome<T> o = general_point<T, N, IS_ND, NINT_LINEAR>(P, pack, q);
             result = o.value;
@@ -1080,7 +1202,8 @@ struct LaunchCfg {
     int strategy;
     int smem_axes;  // stage the axis pack in shared memory
     int all_uniform;  // every axis is uniform and fast-path eligible
-    int all_analytic; // ... and its nodes are exactly g0 + k * h (launch the kernels that compute them)
+    int all_analytic; // ... and its nodes are exactly g0 + k * h (launch the single-pass kernels that compute them)
+    int slab_analytic; // the same for the slab passes
     int slab;         // launch slab_kernel (Params::win_*) instead of interp_kernel
     unsigned smem_bytes;
     int sm_count;

@@ -33,6 +33,7 @@ cudaError_t launch_fixed<NINT_T>(const Params<NINT_T>& P, const LaunchCfg& cfg) 
         default: return cudaErrorInvalidValue;
         }
     }
+    if (cfg.ndim == 1 && cfg.strategy == NINT_LINEAR && P.fused != nullptr) return launch_fused1d<NINT_T, false>(P, cfg);
     switch (cfg.ndim) {
     case 1:
         if (cfg.strategy == NINT_LEFT_NEAREST) return dispatch_smem<NINT_T, 1, NINT_LEFT_NEAREST>(P, cfg);

@@ -35,6 +35,7 @@ cudaError_t launch_nd<NINT_T>(const Params<NINT_T>& P, const LaunchCfg& cfg) {
         default: return cudaErrorInvalidValue;
         }
     }
+    if (cfg.ndim == 1 && cfg.strategy == NINT_LINEAR && P.fused != nullptr) return launch_fused1d<NINT_T, true>(P, cfg);
     switch (cfg.ndim) {
     case 1: return dispatch_nd<NINT_T, 1>(P, cfg);
     case 2: return dispatch_nd<NINT_T, 2>(P, cfg);

@@ -56,10 +56,47 @@ cudaError_t launch_one(const Params<T>& P, const LaunchCfg& cfg) {
     return launch_uni<T, N, IS_ND, STRAT, SMEM, kPrePlain>(P, cfg);
 }
 
+// 1-D Linear from the fused shared-memory pack (Params::fused).
+template <class T, bool IS_ND, int PRE, bool UNI>
+cudaError_t launch_fused1d_variant(const Params<T>& P, const LaunchCfg& cfg) {
+    auto kern = interp1d_fused_kernel<T, IS_ND, PRE, UNI>;
+    const unsigned smem = P.fused_bytes;
+    if (smem > 40u * 1024u) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    static thread_local unsigned cached_smem = ~0u;
+    static thread_local int cached_bps = 0;
+    int bps = cached_bps;
+    if (cached_smem != smem || bps == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kBlock, smem);
+        if (e != cudaSuccess) return e;
+        if (bps < 1) bps = 1;
+        cached_bps = bps;
+        cached_smem = smem;
+    }
+    const unsigned long long want = (P.n + kBlock - 1) / kBlock;
+    const unsigned long long cap = (unsigned long long)cfg.sm_count * (unsigned long long)bps;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (grid == 0) return cudaSuccess;
+    kern<<<grid, kBlock, smem, (cudaStream_t)cfg.stream>>>(P);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+template <class T, bool IS_ND>
+cudaError_t launch_fused1d(const Params<T>& P, const LaunchCfg& cfg) {
+    const bool uni = cfg.all_uniform != 0;
+    if (P.extrap == NINT_EXTRAPOLATE_CLAMP)
+        return uni ? launch_fused1d_variant<T, IS_ND, kPreClamp, true>(P, cfg) : launch_fused1d_variant<T, IS_ND, kPreClamp, false>(P, cfg);
+    if (P.extrap == NINT_EXTRAPOLATE_WRAP)
+        return uni ? launch_fused1d_variant<T, IS_ND, kPreWrap, true>(P, cfg) : launch_fused1d_variant<T, IS_ND, kPreWrap, false>(P, cfg);
+    return uni ? launch_fused1d_variant<T, IS_ND, kPrePlain, true>(P, cfg) : launch_fused1d_variant<T, IS_ND, kPrePlain, false>(P, cfg);
+}
+
 // Slab passes (Linear only, axes in shared memory, policy Clamp or one that leaves the fast path alone).
-template <class T, int N, bool IS_ND, int PRE, bool UNI>
+template <class T, int N, bool IS_ND, int PRE, bool UNI, bool ANA = false>
 cudaError_t launch_slab_variant(const Params<T>& P, const LaunchCfg& cfg) {
-    auto kern = slab_kernel<T, N, IS_ND, PRE, UNI>;
+    auto kern = slab_kernel<T, N, IS_ND, PRE, UNI, ANA>;
     const unsigned smem = cfg.smem_bytes;
     if (smem > 40u * 1024u) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -86,6 +123,12 @@ cudaError_t launch_slab_variant(const Params<T>& P, const LaunchCfg& cfg) {
 template <class T, int N, bool IS_ND>
 cudaError_t launch_slab(const Params<T>& P, const LaunchCfg& cfg) {
     const bool uni = cfg.all_uniform != 0;
+    if constexpr (N == 3 && !IS_ND) {  // analytic axes (nodes computed, IEEE division): the hard-coded 3-D interpolator only
+        if (uni && cfg.slab_analytic) {
+            if (P.extrap == NINT_EXTRAPOLATE_CLAMP) return launch_slab_variant<T, N, IS_ND, kPreClamp, true, true>(P, cfg);
+            return launch_slab_variant<T, N, IS_ND, kPrePlain, true, true>(P, cfg);
+        }
+    }
     if (P.extrap == NINT_EXTRAPOLATE_CLAMP)
         return uni ? launch_slab_variant<T, N, IS_ND, kPreClamp, true>(P, cfg) : launch_slab_variant<T, N, IS_ND, kPreClamp, false>(P, cfg);
     return uni ? launch_slab_variant<T, N, IS_ND, kPrePlain, true>(P, cfg) : launch_slab_variant<T, N, IS_ND, kPrePlain, false>(P, cfg);
