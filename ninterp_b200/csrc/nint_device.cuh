@@ -929,6 +929,7 @@ template <class T, bool IS_ND, int PRE, bool UNI>
 __global__ void __launch_bounds__(kBlock, 4) interp1d_fused_kernel(const __grid_constant__ Params<T> P) {
     constexpr int N = 1;
     extern __shared__ __align__(16) unsigned char smem_pack[];
+    if (P.mode_flag != nullptr && *P.mode_flag != P.mode_want) return;  // the other query-order mode runs this batch
     {
         const uint4* src = reinterpret_cast<const uint4*>(P.fused);
         uint4* dst = reinterpret_cast<uint4*>(smem_pack);
@@ -961,27 +962,30 @@ __global__ void __launch_bounds__(kBlock, 4) interp1d_fused_kernel(const __grid_
             k = (int)guess[b];
         }
         k = max(0, min(k, L - 2));
-        T G0, V0, G1, V1, r;
+        // rcp_div: t by the stored reciprocal with two FMA corrections (one more 8-byte shared load); otherwise by IEEE
+        // division (more FP64 instructions, fewer L1 wavefronts).  Both give RN(a / w).
+        const bool rcp_div = P.fused_rcp_off != 0u;
+        T G0, V0, G1, V1, r = T(0);
         ld_rec(pairs + 2 * k, G0, V0);
         ld_rec(pairs + 2 * k + 2, G1, V1);
-        r = rcps[k];
+        if (rcp_div) r = rcps[k];
         T a = p - G0;
-        bool ok = (p < G1) && in_div_window_pos(a);
+        bool ok = (p < G1) && (rcp_div ? in_div_window_pos(a) : (G0 < p));
         if (!UNI) {
             if (!ok && k < L - 2 && p > G1) {  // the bucket's left edge was in the previous cell: once more with the next
                 ++k;
                 G0 = G1;
                 V0 = V1;
                 ld_rec(pairs + 2 * k + 2, G1, V1);
-                r = rcps[k];
+                if (rcp_div) r = rcps[k];
                 a = p - G0;
-                ok = (p < G1) && in_div_window_pos(a);
+                ok = (p < G1) && (rcp_div ? in_div_window_pos(a) : (G0 < p));
             }
         }
         unsigned status = NINT_STATUS_OK;
         T result;
         if (ok) {
-            const T t = div_markstein<T>(a, G1 - G0, r);
+            const T t = rcp_div ? div_markstein<T>(a, G1 - G0, r) : a / (G1 - G0);
             result = V0 * (T(1) - t) + V1 * t;  // one/strategies.rs:28
         } else {
             Point<T, N> qq;
@@ -1044,7 +1048,11 @@ constexpr unsigned kSlabSpan = 32u * kSlabPer;  // points a warp scans at a time
 // headline workload; at 80 registers (3 CTAs, no spills) 32.7; at 96 (2 CTAs) 31.4; at 48 (5 CTAs) 25.6.
 constexpr int slab_ctas(int n, int elem_bytes) { return n <= 3 ? 3 : min_ctas(n, elem_bytes); }
 
-template <class T, int N, bool IS_ND, int PRE, bool UNI, bool ANA = false>
+// INR (Fill and Error only): one pass over the whole batch in which the members are the points inside the grid on every
+// axis; the others are finished by the scan itself (fill value, or NaN + ExtrapolateError status: n/mod.rs:294-298,
+// 326-337).  With most of a batch out of range (BASELINE config 4: 87 %) the corner gathers then run with full warps
+// instead of four lanes in 32, and nobody calls the out-of-line general path for an out-of-range point.
+template <class T, int N, bool IS_ND, int PRE, bool UNI, bool ANA = false, bool INR = false>
 __global__ void __launch_bounds__(kBlock, slab_ctas(N, (int)sizeof(T))) slab_kernel(const __grid_constant__ Params<T> P) {
     extern __shared__ __align__(16) unsigned char smem_pack[];
     __shared__ unsigned short s_list[kBlock / 32][kSlabSpan];
@@ -1078,7 +1086,7 @@ __global__ void __launch_bounds__(kBlock, slab_ctas(N, (int)sizeof(T))) slab_ker
         for (int d = 0; d < N; ++d) p[d] = (PRE == kPreClamp) ? clamp_coord(q.v[d], P.g0[d], P.gl[d]) : q.v[d];
         unsigned status = NINT_STATUS_OK;
         T result;
-        const bool ok = fast_point<T, N, IS_ND, NINT_LINEAR, UNI, PRE == kPreClamp, true, ANA>(P, pack, pol, p, result);
+        const bool ok = fast_point<T, N, IS_ND, NINT_LINEAR, UNI, PRE == kPreClamp, !INR, ANA>(P, pack, pol, p, result);
         if (!ok) {
             const Outcome<T> o = general_point<T, N, IS_ND, NINT_LINEAR>(P, pack, q);
             result = o.value;
@@ -1096,26 +1104,59 @@ __global__ void __launch_bounds__(kBlock, slab_ctas(N, (int)sizeof(T))) slab_ker
 
     for (unsigned span = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); span < nspans; span += warps) {
         const unsigned base = span * kSlabSpan;
-        // axis-0 coordinates of the span, all requested before the first is used
-        T xs[kSlabPer];
-#pragma unroll
-        for (int r = 0; r < kSlabPer; ++r) {
-            const unsigned j = base + r * 32u + lane;
-            xs[r] = (j < n) ? ld_stream(P.coords[0] + (size_t)j * P.coord_stride) : quiet_nan<T>();
-        }
-        // members: axis-0 coordinate in (win_lo_x, win_hi_x]; the first window also takes everything below and
-        // NaN, the last everything above.  Listed as offsets into the span, in any order.
         unsigned count = 0;
+        if (INR) {
+            // members: inside the grid on every axis (NaN is outside: three/mod.rs:198-201).  The scan loads whole
+            // points, normal priority: the members read theirs again a moment later.
 #pragma unroll
-        for (int r = 0; r < kSlabPer; ++r) {
-            const unsigned j = base + r * 32u + lane;
-            const T x = xs[r];
-            const bool above = P.win_first ? true : (x > P.win_lo_x);
-            const bool below = P.win_last ? true : !(x > P.win_hi_x);
-            const bool mine = (j < n) && above && below;
-            const unsigned bal = __ballot_sync(0xffffffffu, mine);
-            if (mine) list[count + __popc(bal & lt)] = (unsigned short)(r * 32u + lane);
-            count += __popc(bal);
+            for (int r = 0; r < kSlabPer; ++r) {
+                const unsigned j = base + r * 32u + lane;
+                bool inside = j < n;
+                if (j < n) {
+#pragma unroll
+                    for (int d = 0; d < N; ++d) {
+                        const T c = __ldg(P.coords[d] + (size_t)j * P.coord_stride);
+                        inside = inside && (P.g0[d] <= c && c <= P.gl[d]);
+                    }
+                }
+                const bool outside = (j < n) && !inside;
+                if (outside) {
+                    const bool err = P.extrap == NINT_EXTRAPOLATE_ERROR;
+                    st_stream(P.out + j, err ? quiet_nan<T>() : P.fill);
+                    if (P.status) P.status[j] = (uint8_t)(err ? NINT_STATUS_EXTRAPOLATE_ERROR : NINT_STATUS_OK);
+                }
+                if (P.extrap == NINT_EXTRAPOLATE_ERROR) {  // warp-uniform
+                    const unsigned eb = __ballot_sync(0xffffffffu, outside);
+                    if (eb != 0u && lane == 0u) {
+                        atomicAdd(&s_info[0], (unsigned long long)__popc(eb));
+                        atomicMin(&s_info[2], (unsigned long long)(base + r * 32u + (unsigned)(__ffs(eb) - 1)) + P.index_base);
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, inside);
+                if (inside) list[count + __popc(bal & lt)] = (unsigned short)(r * 32u + lane);
+                count += __popc(bal);
+            }
+        } else {
+            // axis-0 coordinates of the span, all requested before the first is used
+            T xs[kSlabPer];
+#pragma unroll
+            for (int r = 0; r < kSlabPer; ++r) {
+                const unsigned j = base + r * 32u + lane;
+                xs[r] = (j < n) ? ld_stream(P.coords[0] + (size_t)j * P.coord_stride) : quiet_nan<T>();
+            }
+            // members: axis-0 coordinate in (win_lo_x, win_hi_x]; the first window also takes everything below and
+            // NaN, the last everything above.  Listed as offsets into the span, in any order.
+#pragma unroll
+            for (int r = 0; r < kSlabPer; ++r) {
+                const unsigned j = base + r * 32u + lane;
+                const T x = xs[r];
+                const bool above = P.win_first ? true : (x > P.win_lo_x);
+                const bool below = P.win_last ? true : !(x > P.win_hi_x);
+                const bool mine = (j < n) && above && below;
+                const unsigned bal = __ballot_sync(0xffffffffu, mine);
+                if (mine) list[count + __popc(bal & lt)] = (unsigned short)(r * 32u + lane);
+                count += __popc(bal);
+            }
         }
         __syncwarp();
         // groups of 32: the waiting members first, the rest from the list; the coordinates of the next group
@@ -1205,6 +1246,7 @@ struct LaunchCfg {
     int all_analytic; // ... and its nodes are exactly g0 + k * h (launch the single-pass kernels that compute them)
     int slab_analytic; // the same for the slab passes
     int slab;         // launch slab_kernel (Params::win_*) instead of interp_kernel
+    int inrange;      // ... in its one-pass form whose members are the in-range points (Fill, Error)
     unsigned smem_bytes;
     int sm_count;
     void* stream;

@@ -94,9 +94,9 @@ cudaError_t launch_fused1d(const Params<T>& P, const LaunchCfg& cfg) {
 }
 
 // Slab passes (Linear only, axes in shared memory, policy Clamp or one that leaves the fast path alone).
-template <class T, int N, bool IS_ND, int PRE, bool UNI, bool ANA = false>
+template <class T, int N, bool IS_ND, int PRE, bool UNI, bool ANA = false, bool INR = false>
 cudaError_t launch_slab_variant(const Params<T>& P, const LaunchCfg& cfg) {
-    auto kern = slab_kernel<T, N, IS_ND, PRE, UNI, ANA>;
+    auto kern = slab_kernel<T, N, IS_ND, PRE, UNI, ANA, INR>;
     const unsigned smem = cfg.smem_bytes;
     if (smem > 40u * 1024u) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -123,6 +123,10 @@ cudaError_t launch_slab_variant(const Params<T>& P, const LaunchCfg& cfg) {
 template <class T, int N, bool IS_ND>
 cudaError_t launch_slab(const Params<T>& P, const LaunchCfg& cfg) {
     const bool uni = cfg.all_uniform != 0;
+    if constexpr (N >= 4 && IS_ND) {  // in-range compaction: InterpND with four or more axes, Fill and Error
+        if (cfg.inrange) return uni ? launch_slab_variant<T, N, IS_ND, kPrePlain, true, false, true>(P, cfg)
+                                    : launch_slab_variant<T, N, IS_ND, kPrePlain, false, false, true>(P, cfg);
+    }
     if constexpr (N == 3 && !IS_ND) {  // analytic axes (nodes computed, IEEE division): the hard-coded 3-D interpolator only
         if (uni && cfg.slab_analytic) {
             if (P.extrap == NINT_EXTRAPOLATE_CLAMP) return launch_slab_variant<T, N, IS_ND, kPreClamp, true, true>(P, cfg);
