@@ -269,6 +269,7 @@ def test_slab_passes_and_order_probe(monkeypatch):
 
     monkeypatch.setenv("NINT_SLAB_MIN_BYTES", "0")
     monkeypatch.setenv("NINT_SLAB_MIN_POINTS", "0")
+    monkeypatch.setenv("NINT_COMPACT", "0")  # 4-D Fill/Error batches would otherwise take the in-range compaction pass
     rng = np.random.default_rng(99)
     n = 300_001
     for kind, lens, dtype, mode, passes in [(FIXED, (40, 9, 7), np.float64, "uniform", 3), (FIXED, (33, 12), np.float32, "nonuniform", 2),
@@ -314,6 +315,28 @@ def test_slab_passes_and_order_probe(monkeypatch):
     got, st, _ = gpu_eval(g, cols)
     assert_same(got, st, *o.eval(cols), "wrap stays single pass")
     assert _lib.lib().nint_last_query_order(g._h) == 0
+
+
+def test_inrange_compaction_pass():
+    # InterpND with four or more axes under Fill / Error: the scan finishes the out-of-range points itself and the
+    # in-range ones are compacted into full warps before their 2^N corners are gathered (slab_kernel<INR>)
+    from gpu_util import assert_same, expected_info, gpu_eval, make_pair
+
+    rng = np.random.default_rng(808)
+    for lens, dtype, mode in [((6, 5, 7, 4), np.float64, "nonuniform"), ((5, 4, 6, 3, 4), np.float32, "nonuniform"),
+                              ((4, 3, 3, 4, 3, 3), np.float64, "uniform"), ((9, 3, 1, 4), np.float32, "nonuniform")]:
+        axes = _axes(rng, lens, dtype, mode)
+        values = rng.uniform(-1, 1, lens).astype(dtype)
+        for n in (70_001, 300_000):
+            cols = _queries(rng, axes, n, dtype, 0.2)   # +-30 % of the span: most points are outside on some axis
+            for extrap in (FILL, ERROR):
+                g, o = make_pair(ND, axes, values, LIN, extrap, fill=7.25, dtype=dtype)
+                want, st_want = o.eval(cols, nthreads=O.max_threads())
+                got, st, info = gpu_eval(g, cols)
+                assert_same(got, st, want, st_want, f"compaction {lens} {extrap} n={n}")
+                assert info == expected_info(st_want)
+                got, st, _ = gpu_eval(g, cols, aos=True)
+                assert_same(got, st, want, st_want, f"compaction aos {lens} {extrap}")
 
 
 def test_analytic_uniform_axes(monkeypatch):
