@@ -687,6 +687,14 @@ void build_tile(nint_handle* h) {
     g.sh[0] = 4;
     g.sh[1] = (es == 8) ? 4 : 5;
     g.sh[2] = 5;
+    if (const char* env = std::getenv("NINT_TILE_SH")) {  // tuning: "a,b,c" = log2(cells per tile) per axis, at most the default
+        int a = 0, b = 0, c = 0;
+        if (std::sscanf(env, "%d,%d,%d", &a, &b, &c) == 3) {
+            g.sh[0] = std::max(1, std::min(a, g.sh[0]));
+            g.sh[1] = std::max(1, std::min(b, g.sh[1]));
+            g.sh[2] = std::max(1, std::min(c, g.sh[2]));
+        }
+    }
     unsigned long long ntiles = 1, vol = 1;
     for (int d = 0; d < 3; ++d) {
         const int cells = (int)h->axis_len[d] - 1;
