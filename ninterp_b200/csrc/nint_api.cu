@@ -737,7 +737,7 @@ void build_tile(nint_handle* h) {
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = ((EncodeFn)fn)(&h->tile_map, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                                       h->d_values, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,  // box rows are 272 B: promoted to 256 B they fetch 512
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return;
     if (!h->pool) {
@@ -863,13 +863,11 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     for (int d = 0; d < h->ndim_eff; ++d)
         if ((h->ax[d].flags & (nint::kAxisUniform | nint::kAxisFast)) != (nint::kAxisUniform | nint::kAxisFast)) cfg.all_uniform = 0;
     // NINT_ANALYTIC=1: coherent single pass with computed nodes (measured: see DESIGN.md); the bin kernel always uses them
-    cfg.all_analytic = 0;
-    if (const char* env = std::getenv("NINT_ANALYTIC")) {
-        if (std::atoi(env)) {
-            cfg.all_analytic = 1;
-            for (int d = 0; d < h->ndim_eff; ++d)
-                if (!(h->ax[d].flags & nint::kAxisAnalytic)) cfg.all_analytic = 0;
-        }
+    {
+        const char* env = std::getenv("NINT_ANALYTIC");
+        cfg.all_analytic = env ? (std::atoi(env) != 0) : !h->smem_axes;  // default: only when the pack is not staged
+        for (int d = 0; d < h->ndim_eff; ++d)
+            if (!(h->ax[d].flags & nint::kAxisAnalytic)) cfg.all_analytic = 0;
     }
     cfg.slab_analytic = 0;
     if (const char* env = std::getenv("NINT_SLAB_ANALYTIC")) {

@@ -638,8 +638,8 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
         ok = fast_weights_analytic<T, N, IS_ND, FIRST>(P, p, k, t);
         if (N >= 4 && !ok) return false;
         T cube[1 << N];
-        if (!PLAIN) {
-            unsigned cell = 0;  // the analytic single-pass kernels are only dispatched when the cell-packed table exists
+        if (!PLAIN && P.cells != nullptr) {
+            unsigned cell = 0;
 #pragma unroll
             for (int d = 0; d < N; ++d) cell += (unsigned)k[d] * (unsigned)P.cstride[d];
             ld_cells<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
@@ -662,6 +662,25 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
             for (int j = 0; j < half; ++j) cube[j] = cube[j] * sd + cube[half + j] * td;
         }
         result = cube[0];
+        return ok;
+    }
+    if (ANA && STRAT != NINT_LINEAR) {
+        // Nearest family on analytic axes: the bracket g[k] < p <= g[k+1] from computed nodes, then the same choice
+        // between l and l + 1 (three/strategies.rs:70-74; one/strategies.rs:79, :102)
+        long long off = 0;
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            int kd = to_int_sat((p[d] - P.g0[d]) * P.inv_h[d]);
+            kd = max(0, min(kd, P.L[d] - 2));
+            const T G0 = P.g0[d] + (T)kd * P.h[d];
+            const T G1 = P.g0[d] + (T)(kd + 1) * P.h[d];
+            ok = ok && (G0 < p[d]) && (kCollapse ? (p[d] < G1) : (p[d] <= G1));
+            int idx = kd;
+            if (STRAT == NINT_NEAREST) idx += ((p[d] - G0) < (G1 - p[d])) ? 0 : 1;
+            if (STRAT == NINT_RIGHT_NEAREST) idx += 1;
+            off += (long long)idx * P.vstride[d];
+        }
+        result = ld_table(P.values + off, pol);  // idx <= L-1 on every axis: inside the table even if !ok
         return ok;
     }
 #pragma unroll

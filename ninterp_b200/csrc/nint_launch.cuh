@@ -41,9 +41,12 @@ cudaError_t launch_variant(const Params<T>& P, const LaunchCfg& cfg) {
 // their axis pack lives.
 template <class T, int N, bool IS_ND, int STRAT, bool SMEM, int PRE>
 cudaError_t launch_uni(const Params<T>& P, const LaunchCfg& cfg) {
-    // analytic axes: only the hard-coded 2-D/3-D Linear interpolators with axes in shared memory get the extra kernels
-    if constexpr (STRAT == NINT_LINEAR && SMEM && !IS_ND && (N == 2 || N == 3)) {
-        if (cfg.all_uniform && cfg.all_analytic && P.cells != nullptr) return launch_variant<T, N, IS_ND, STRAT, SMEM, PRE, true, true>(P, cfg);
+    // Analytic axes (nodes computed, not loaded): the hard-coded 2-D/3-D interpolators get the extra kernels.  With
+    // the axis pack in shared memory they are opt-in (NINT_ANALYTIC=1: faster where the L1 data pipe is the limit,
+    // slower on cell-ordered batches); with a pack too large for shared memory every record load is an L1 wavefront
+    // per lane, and computing the nodes is the default (2048^2, Clamp: see DESIGN.md).
+    if constexpr (!IS_ND && (N == 2 || N == 3) && (STRAT == NINT_LINEAR || STRAT == NINT_NEAREST)) {
+        if (cfg.all_uniform && cfg.all_analytic) return launch_variant<T, N, IS_ND, STRAT, SMEM, PRE, true, true>(P, cfg);
     }
     if (cfg.all_uniform && (STRAT != NINT_LINEAR || P.cells != nullptr))
         return launch_variant<T, N, IS_ND, STRAT, SMEM, PRE, true>(P, cfg);

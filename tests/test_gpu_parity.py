@@ -351,11 +351,23 @@ def test_analytic_uniform_axes(monkeypatch):
         axes = _axes(rng, lens, dtype, "analytic")
         values = rng.uniform(-1, 1, lens).astype(dtype)
         cols = _queries(rng, axes, 200_000, dtype, 0.1)
-        for extrap in (ERROR, CLAMP, ENABLE, FILL, WRAP):
-            g, o = make_pair(kind, axes, values, LIN, extrap, fill=0.5, dtype=dtype)
+        for strat, extrap in [(LIN, e) for e in (ERROR, CLAMP, ENABLE, FILL, WRAP)] + [(NEA, e) for e in (ERROR, CLAMP, FILL, WRAP)]:
+            g, o = make_pair(kind, axes, values, strat, extrap, fill=0.5, dtype=dtype)
             got, st, info = gpu_eval(g, cols)
             want, st_want = o.eval(cols, nthreads=O.max_threads())
-            assert_same(got, st, want, st_want, f"analytic {lens} {dtype.__name__} {extrap}")
+            assert_same(got, st, want, st_want, f"analytic {lens} {dtype.__name__} {strat} {extrap}")
+            assert info == expected_info(st_want)
+    # an axis pack too large for shared memory: computed nodes are the default there (no environment variable)
+    monkeypatch.delenv("NINT_ANALYTIC")
+    for lens, dtype in [((6000, 5), np.float64), ((3000, 7, 3), np.float64), ((9000, 4), np.float32)]:
+        axes = _axes(rng, lens, dtype, "analytic")
+        values = rng.uniform(-1, 1, lens).astype(dtype)
+        cols = _queries(rng, axes, 200_000, dtype, 0.1)
+        for strat, extrap in [(LIN, CLAMP), (LIN, ERROR), (NEA, CLAMP), (NEA, WRAP)]:
+            g, o = make_pair(FIXED, axes, values, strat, extrap, dtype=dtype)
+            got, st, info = gpu_eval(g, cols)
+            want, st_want = o.eval(cols, nthreads=O.max_threads())
+            assert_same(got, st, want, st_want, f"analytic, pack in global memory {lens} {dtype.__name__} {strat} {extrap}")
             assert info == expected_info(st_want)
 
 

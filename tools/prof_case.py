@@ -56,7 +56,7 @@ def main():
         G2 = a.grid if a.grid != 256 else 2048
         axes = [np.arange(float(G2))] * 2
         values = rng.uniform(0, 1, (G2, G2))
-        g = nb.Interp2D(*axes, values, nb.strategy.Linear, nb.Extrapolate.Clamp)
+        g = nb.Interp2D(*axes, values, nb.strategy.Nearest if a.strategy == "nearest" else nb.strategy.Linear, nb.Extrapolate.Clamp)
         cols = [torch.rand(n, dtype=torch.float64, device=dev) * (G2 - 1) * 1.1 - 0.05 * (G2 - 1) for _ in range(2)]
         tdt = torch.float64
     else:
