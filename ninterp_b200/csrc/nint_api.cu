@@ -865,7 +865,7 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     // NINT_ANALYTIC=1: coherent single pass with computed nodes (measured: see DESIGN.md); the bin kernel always uses them
     {
         const char* env = std::getenv("NINT_ANALYTIC");
-        cfg.all_analytic = env ? (std::atoi(env) != 0) : !h->smem_axes;  // default: only when the pack is not staged
+        cfg.all_analytic = env ? (std::atoi(env) != 0) : 0;  // opt-in: measured slower on the BASELINE configurations
         for (int d = 0; d < h->ndim_eff; ++d)
             if (!(h->ax[d].flags & nint::kAxisAnalytic)) cfg.all_analytic = 0;
     }

@@ -543,11 +543,16 @@ __device__ __forceinline__ bool guess_cell(const AxisRef<T>& a, const unsigned* 
 // axis).  A verified cell is the cell the reference picks: find_nearest_index returns the cell to the left
 // of an exact hit and maps `== last` to L-2, both of which satisfy the same inequality when the nodes are
 // strictly increasing; and it implies that p is in range and not NaN.
-template <class T, bool STRICT>
+// FIRST (hard-coded Nearest under Clamp only): p == g[0] in the first cell is accepted too.  Clamping produces that
+// coordinate for every point below the grid, and find_nearest_index(g, g[0]) = 0 with (p - g[0]) < (g[1] - p), so the
+// reference picks index 0 (three/strategies.rs:69-74) -- what the fast path computes from k = 0.  Without the clause a
+// batch with a few per cent of its points below the grid sends a lane of nearly every warp to the general path.
+template <class T, bool STRICT, bool FIRST = false>
 __device__ __forceinline__ bool verify_cell(const AxisRef<T>& a, T p, int k, T& G0, T& G1, T& R) {
     ld_rec(a.rec + 2 * k, G0, R);
     G1 = a.g(k + 1);
-    return (G0 < p) && (STRICT ? (p < G1) : (p <= G1));
+    const bool lower = (G0 < p) || (FIRST && !STRICT && k == 0 && p == G0);
+    return lower && (STRICT ? (p < G1) : (p <= G1));
 }
 
 // Verification for Linear plus the division-window test on a = p - g[k].  Besides g[k] < p <= g[k+1] the
@@ -587,13 +592,13 @@ __device__ __forceinline__ bool verify_linear_retry(const AxisRef<T>& ax, T p, i
     }
     return ok;
 }
-template <class T, bool STRICT, bool UNI>
+template <class T, bool STRICT, bool UNI, bool FIRST = false>
 __device__ __forceinline__ bool verify_retry(const AxisRef<T>& ax, T p, int& k, T& G0, T& G1, T& R) {
-    bool ok = verify_cell<T, STRICT>(ax, p, k, G0, G1, R);
+    bool ok = verify_cell<T, STRICT, FIRST>(ax, p, k, G0, G1, R);
     if (!UNI) {
         if (!ok && !(ax.flags & kAxisUniform) && k < ax.L - 2 && p > G1) {
             ++k;
-            ok = verify_cell<T, STRICT>(ax, p, k, G0, G1, R);
+            ok = verify_cell<T, STRICT, FIRST>(ax, p, k, G0, G1, R);
         }
     }
     return ok;
@@ -674,7 +679,8 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
             kd = max(0, min(kd, P.L[d] - 2));
             const T G0 = P.g0[d] + (T)kd * P.h[d];
             const T G1 = P.g0[d] + (T)(kd + 1) * P.h[d];
-            ok = ok && (G0 < p[d]) && (kCollapse ? (p[d] < G1) : (p[d] <= G1));
+            const bool lower = (G0 < p[d]) || (FIRST && STRAT == NINT_NEAREST && !kCollapse && kd == 0 && p[d] == G0);
+            ok = ok && lower && (kCollapse ? (p[d] < G1) : (p[d] <= G1));
             int idx = kd;
             if (STRAT == NINT_NEAREST) idx += ((p[d] - G0) < (G1 - p[d])) ? 0 : 1;
             if (STRAT == NINT_RIGHT_NEAREST) idx += 1;
@@ -751,7 +757,7 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
 #pragma unroll
         for (int d = 0; d < N; ++d) {
             T G0, G1, r;
-            ok = verify_cell<T, kCollapse>(load_axis<T>(P, pack, d), p[d], k[d], G0, G1, r) && ok;
+            ok = verify_cell<T, kCollapse, FIRST && STRAT == NINT_NEAREST>(load_axis<T>(P, pack, d), p[d], k[d], G0, G1, r) && ok;
             int idx = k[d];
             if (STRAT == NINT_NEAREST) idx += ((p[d] - G0) < (G1 - p[d])) ? 0 : 1;  // tie -> upper (three/strategies.rs:70-74)
             if (STRAT == NINT_RIGHT_NEAREST) idx += 1;
@@ -763,7 +769,7 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
 #pragma unroll
             for (int d = 0; d < N; ++d) {
                 T G0, G1, r;
-                ok = verify_retry<T, kCollapse, UNI>(load_axis<T>(P, pack, d), p[d], k[d], G0, G1, r) && ok;
+                ok = verify_retry<T, kCollapse, UNI, FIRST && STRAT == NINT_NEAREST>(load_axis<T>(P, pack, d), p[d], k[d], G0, G1, r) && ok;
                 int idx = k[d];
                 if (STRAT == NINT_NEAREST) idx += ((p[d] - G0) < (G1 - p[d])) ? 0 : 1;
                 if (STRAT == NINT_RIGHT_NEAREST) idx += 1;

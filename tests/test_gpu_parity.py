@@ -357,8 +357,7 @@ def test_analytic_uniform_axes(monkeypatch):
             want, st_want = o.eval(cols, nthreads=O.max_threads())
             assert_same(got, st, want, st_want, f"analytic {lens} {dtype.__name__} {strat} {extrap}")
             assert info == expected_info(st_want)
-    # an axis pack too large for shared memory: computed nodes are the default there (no environment variable)
-    monkeypatch.delenv("NINT_ANALYTIC")
+    # the same with an axis pack too large for shared memory
     for lens, dtype in [((6000, 5), np.float64), ((3000, 7, 3), np.float64), ((9000, 4), np.float32)]:
         axes = _axes(rng, lens, dtype, "analytic")
         values = rng.uniform(-1, 1, lens).astype(dtype)
