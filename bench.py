@@ -545,8 +545,8 @@ def run_b200(args, rank, local_rank, world):
         status = torch.empty(n, dtype=torch.uint8, device=dev)
         variants["random_queries_with_status_mask"] = timed(interp, cols, out, status=status, bpp=33, oracle=o3, sample=16_000_000)
         del status
-        # cfg 3 forced onto the older routes, for the record
-        for name, route_env in (("random_queries_slab_passes", "slab"), ("random_queries_single_pass", "single")):
+        # cfg 3 forced onto the other routes, for the record: binned tiles (TMA-staged, nint_tile.cuh) and the single pass
+        for name, route_env in (("random_queries_binned_tiles", "tile"), ("random_queries_single_pass", "single")):
             os.environ["NINT_ROUTE"] = route_env
             variants[name] = timed(interp, cols, out, steps=5)
             os.environ.pop("NINT_ROUTE", None)
