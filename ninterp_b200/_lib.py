@@ -9,7 +9,9 @@ import ctypes as C
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-SO = PKG / "libninterp_cuda.so"
+# NINT_LIB_VARIANT=checked selects the bounds-checked build (see build.py)
+_VARIANT = __import__("os").environ.get("NINT_LIB_VARIANT", "")
+SO = PKG / ("libninterp_cuda" + ("_" + _VARIANT if _VARIANT else "") + ".so")
 
 # enums of include/ninterp_cuda.h
 F32, F64 = 0, 1

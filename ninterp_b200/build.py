@@ -16,8 +16,11 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-OBJ = PKG / "_build"
-SO = PKG / "libninterp_cuda.so"
+# NINT_LIB_VARIANT=checked builds (and ninterp_b200._lib loads) libninterp_cuda_checked.so: the same sources with
+# -DNINT_BOUNDS_CHECK, every index checked on the device (csrc/nint_device.cuh)
+VARIANT = os.environ.get("NINT_LIB_VARIANT", "")
+OBJ = PKG / ("_build" + ("_" + VARIANT if VARIANT else ""))
+SO = PKG / ("libninterp_cuda" + ("_" + VARIANT if VARIANT else "") + ".so")
 
 SOURCES = ["nint_api.cu", "nint_fixed_f64.cu", "nint_fixed_f32.cu", "nint_nd_f64.cu", "nint_nd_f32.cu", "nint_tile_f64.cu", "nint_tile_f32.cu", "nint_selftest.cu"]
 NVCC_FLAGS = [
@@ -54,6 +57,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
     OBJ.mkdir(exist_ok=True)
     extra = os.environ.get("NINT_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DNINT_MIN_CTAS=3
+    if VARIANT == "checked":
+        extra.append("-DNINT_BOUNDS_CHECK")
 
     def compile_one(src: str):
         obj = OBJ / (src + ".o")

@@ -124,6 +124,7 @@ struct nint_handle {
     size_t values_len = 1;
     void* d_values = nullptr;
     void* d_cells = nullptr;  // cell-packed copy of the table for Linear (2^N corners per cell), or NULL
+    unsigned long long ncells = 0;
     unsigned char* d_pack = nullptr;
     unsigned char* d_fused = nullptr;  // 1-D Linear: {node, value} pairs, reciprocals and guess table for shared memory
     unsigned fused_bytes = 0, fused_rcp_off = 0, fused_guess_off = 0;
@@ -572,6 +573,7 @@ int build_cells(nint_handle* h) {
         return cuda_fail(e, "pack_cells");
     }
     h->d_cells = out;
+    h->ncells = cells;
     return NINT_OK;
 }
 
@@ -579,6 +581,8 @@ template <class T>
 void fill_params(const nint_handle* h, nint::Params<T>& P) {
     std::memset(&P, 0, sizeof P);
     P.values = (const T*)h->d_values;
+    P.values_len = h->values_len;
+    P.ncells = h->ncells;
     P.cells = (h->strategy == NINT_LINEAR) ? (const T*)h->d_cells : nullptr;
     P.pack = h->d_pack;
     P.pack_bytes = h->pack_hot_bytes;
@@ -795,6 +799,7 @@ int launch_tiles(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
     }
     G.cursor = (unsigned*)scratch;
     G.records = scratch + ((cursor_bytes + 255) & ~(size_t)255);
+    G.records_bytes = record_bytes;
     nint::TileLaunch tl;
     tl.is_nd = cfg.is_nd;
     tl.all_uniform = cfg.all_uniform;
@@ -839,7 +844,8 @@ int launch_tiles(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
 
 template <class T>
 int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride, size_t n, void* out,
-                 uint8_t* status, nint_batch_info* info_dev, unsigned long long index_base, cudaStream_t stream) {
+                 uint8_t* status, nint_batch_info* info_dev, unsigned long long index_base, cudaStream_t stream,
+                 bool pipeline_chunk) {
     if (h->constant) {
         cudaError_t e = nint::launch_constant<T>((const T*)h->d_values, (T*)out, status, n, h->sm_count, stream);
         if (e != cudaSuccess) return cuda_fail(e, "constant kernel launch");
@@ -882,8 +888,10 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     cfg.stream = stream;
     cfg.slab = 0;
     cfg.inrange = 0;
-    int windows = slab_windows(h, n);
-    const bool tile = tile_route(h, n, windows);
+    // Chunks of the host pipeline are bound by the PCIe copies around them (a 4 Mi-point chunk is ~2.3 ms of copies
+    // against 0.2 ms of single pass): no order probe, no multi-launch routes there.
+    int windows = pipeline_chunk ? 0 : slab_windows(h, n);
+    const bool tile = pipeline_chunk ? false : tile_route(h, n, windows);
     h->last_route.store(0, std::memory_order_relaxed);
     // InterpND with four or more axes under Fill or Error: one pass that compacts the in-range points first (see
     // slab_kernel<INR>); NINT_COMPACT=0 keeps the plain single pass
@@ -953,7 +961,7 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
 }
 
 int launch(nint_handle* h, const void* const* cols, long long coord_stride, size_t n, void* out, uint8_t* status,
-           nint_batch_info* info_dev, unsigned long long index_base, cudaStream_t stream) {
+           nint_batch_info* info_dev, unsigned long long index_base, cudaStream_t stream, bool pipeline_chunk = false) {
     // the kernels index points with 32 bits: batches beyond kMaxLaunchPoints are split into back-to-back launches
     const size_t es = elem_size(h->dtype);
     for (size_t start = 0; start < n; start += nint::kMaxLaunchPoints) {
@@ -963,8 +971,8 @@ int launch(nint_handle* h, const void* const* cols, long long coord_stride, size
         void* o = (unsigned char*)out + start * es;
         uint8_t* st = status ? status + start : nullptr;
         const int rc = (h->dtype == NINT_F64)
-                           ? launch_typed<double>(h, sub, coord_stride, m, o, st, info_dev, index_base + start, stream)
-                           : launch_typed<float>(h, sub, coord_stride, m, o, st, info_dev, index_base + start, stream);
+                           ? launch_typed<double>(h, sub, coord_stride, m, o, st, info_dev, index_base + start, stream, pipeline_chunk)
+                           : launch_typed<float>(h, sub, coord_stride, m, o, st, info_dev, index_base + start, stream, pipeline_chunk);
         if (rc != NINT_OK) return rc;
     }
     return NINT_OK;
@@ -1317,7 +1325,7 @@ int nint_interpolate_batch_host(nint_handle* h, int layout, const void* data, si
         }
         NINT_CUDA_DRAIN(cudaEventRecord(s.in_done, p.s_in));
         NINT_CUDA_DRAIN(cudaStreamWaitEvent(p.s_k, s.in_done, 0));
-        rc = launch(h, cols_dev, stride, m, s.d_out, status_host ? s.d_status : nullptr, h->d_info, start, p.s_k);
+        rc = launch(h, cols_dev, stride, m, s.d_out, status_host ? s.d_status : nullptr, h->d_info, start, p.s_k, true);
         if (rc != NINT_OK) return drain_pipeline(h, rc);
         NINT_CUDA_DRAIN(cudaEventRecord(s.k_done, p.s_k));
         NINT_CUDA_DRAIN(cudaStreamWaitEvent(p.s_out, s.k_done, 0));

@@ -29,6 +29,22 @@
 
 #include "../../include/ninterp_cuda.h"
 
+// -DNINT_BOUNDS_CHECK (python -m ninterp_b200.build with NINT_LIB_VARIANT=checked): every index the kernels form --
+// axis records, guess and bucket tables, value table and cell-packed table offsets, shared-memory lists, record lists
+// and tiles of the binned route -- is checked against its container and the kernel traps on a violation.  This is
+// the stand-in for compute-sanitizer's memcheck, which is closed on the GPU pool: the whole
+// -m gpu suite runs against this build.
+#ifdef NINT_BOUNDS_CHECK
+#define NINT_ASSERT(cond)                   \
+    do {                                    \
+        if (!(cond)) asm volatile("trap;"); \
+    } while (0)
+#else
+#define NINT_ASSERT(cond) \
+    do {                  \
+    } while (0)
+#endif
+
 namespace nint {
 
 constexpr int kMaxDim = NINT_MAX_NDIM;
@@ -56,6 +72,8 @@ struct Params {
     uint8_t* status;
     nint_batch_info* info;
     const T* values;
+    unsigned long long values_len;  // elements of `values` (the allocation has 4 more: ld_pair's slack)
+    unsigned long long ncells;      // cells of `cells`
     const T* cells;              // cell-packed copy of the table (2^N corners per cell, contiguous) or NULL
     const unsigned char* pack;   // axis pack in global memory
     unsigned pack_bytes;         // multiple of 16: records + guess tables, the part staged in shared memory
@@ -96,8 +114,14 @@ struct AxisRef {
     const uint2* lut;  // bucket b -> [lo, hi]: bounds on the node count below any point of the bucket (global memory)
     int L, M, flags;
     T g0, gl, inv_w, inv_h;
-    __device__ __forceinline__ T g(int i) const { return rec[2 * i]; }
-    __device__ __forceinline__ T rcp(int i) const { return rec[2 * i + 1]; }
+    __device__ __forceinline__ T g(int i) const {
+        NINT_ASSERT(i >= 0 && i <= L + 1);
+        return rec[2 * i];
+    }
+    __device__ __forceinline__ T rcp(int i) const {
+        NINT_ASSERT(i >= 0 && i <= L + 1);
+        return rec[2 * i + 1];
+    }
 };
 
 // {g[k], rcp[k]} with one 2-element shared/global load
@@ -210,6 +234,7 @@ __device__ __forceinline__ int count_less(const AxisRef<T>& a, T p) {
     const uint2 e = a.lut[b];
     int lo = (int)e.x;
     int n = (int)e.y - (int)e.x;
+    NINT_ASSERT(b >= 0 && b < a.M && lo >= 0 && n >= 0 && lo + n <= a.L);
     while (n > 0) {
         const int half = n >> 1;
         const bool lt = a.g(lo + half) < p;
@@ -391,6 +416,13 @@ __device__ __forceinline__ T eval_linear(const AxisRef<T> (&ax)[N], const Params
         return T(0);
     }
     T cube[1 << N];
+#ifdef NINT_BOUNDS_CHECK
+    {
+        long long top = base;
+        for (int d = 0; d < N; ++d) top += step[d];
+        NINT_ASSERT(base >= 0 && (unsigned long long)top < P.values_len);
+    }
+#endif
     gather_rows<T, N>(P.values + base, step, pol, fixed[N - 1], cube);
     // reduce axis 0 first, then 1, ...: v_l * (1 - t) + v_u * t, each op rounded separately
 #pragma unroll
@@ -450,6 +482,7 @@ __device__ __forceinline__ T eval_index(const AxisRef<T> (&ax)[N], const Params<
     long long off = 0;
 #pragma unroll
     for (int d = 0; d < N; ++d) off += (long long)idx[d] * P.vstride[d];
+    NINT_ASSERT(off >= 0 && (unsigned long long)off < P.values_len);
     if (LEN1 && single) return ld_table(P.values + off, pol);  // un-collapsed length-1 axes sit at index 0
     if (panic) {
         status = NINT_STATUS_PANIC;
@@ -533,6 +566,7 @@ __device__ __forceinline__ bool guess_cell(const AxisRef<T>& a, const unsigned* 
         // is in it, in the next one, or needs the general path
         int b = to_int_sat((p - a.g0) * a.inv_w);
         b = max(0, min(b, a.M - 1));
+        NINT_ASSERT(b >= 0 && b < a.M);
         k = (int)guess[b];  // bucket -> the cell holding the bucket's left edge
     }
     k = max(0, min(k, a.L - 2));
@@ -549,6 +583,7 @@ __device__ __forceinline__ bool guess_cell(const AxisRef<T>& a, const unsigned* 
 // batch with a few per cent of its points below the grid sends a lane of nearly every warp to the general path.
 template <class T, bool STRICT, bool FIRST = false>
 __device__ __forceinline__ bool verify_cell(const AxisRef<T>& a, T p, int k, T& G0, T& G1, T& R) {
+    NINT_ASSERT(k >= 0 && k <= a.L - 2);
     ld_rec(a.rec + 2 * k, G0, R);
     G1 = a.g(k + 1);
     const bool lower = (G0 < p) || (FIRST && !STRICT && k == 0 && p == G0);
@@ -566,6 +601,7 @@ __device__ __forceinline__ bool verify_cell(const AxisRef<T>& a, T p, int k, T& 
 template <class T, bool STRICT, bool FIRST>
 __device__ __forceinline__ bool verify_cell_linear(const AxisRef<T>& ax, T p, int k, T& a, T& w, T& R) {
     T G0, G1;
+    NINT_ASSERT(k >= 0 && k <= ax.L - 2);
     ld_rec(ax.rec + 2 * k, G0, R);
     G1 = ax.g(k + 1);
     a = p - G0;
@@ -647,6 +683,7 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
             unsigned cell = 0;
 #pragma unroll
             for (int d = 0; d < N; ++d) cell += (unsigned)k[d] * (unsigned)P.cstride[d];
+            NINT_ASSERT((unsigned long long)cell < P.ncells);
             ld_cells<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
         } else {
             long long base = 0;
@@ -656,6 +693,13 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
                 base += (long long)k[d] * P.vstride[d];
                 step[d] = P.vstride[d];
             }
+#ifdef NINT_BOUNDS_CHECK
+            {
+                long long top = base;
+                for (int d = 0; d < N; ++d) top += step[d];
+                NINT_ASSERT(base >= 0 && (unsigned long long)top < P.values_len);
+            }
+#endif
             gather_rows<T, N>(P.values + base, step, pol, false, cube);
         }
 #pragma unroll
@@ -686,6 +730,7 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
             if (STRAT == NINT_RIGHT_NEAREST) idx += 1;
             off += (long long)idx * P.vstride[d];
         }
+        NINT_ASSERT(off >= 0 && (unsigned long long)off < P.values_len);
         result = ld_table(P.values + off, pol);  // idx <= L-1 on every axis: inside the table even if !ok
         return ok;
     }
@@ -730,6 +775,7 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
             unsigned cell = 0;  // build_cells() only packs tables with fewer than 2^31 cells
 #pragma unroll
             for (int d = 0; d < N; ++d) cell += (unsigned)k[d] * (unsigned)P.cstride[d];
+            NINT_ASSERT((unsigned long long)cell < P.ncells);
             ld_cells<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
         } else {
             long long base = 0;
@@ -739,6 +785,13 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
                 base += (long long)k[d] * P.vstride[d];
                 step[d] = P.vstride[d];
             }
+#ifdef NINT_BOUNDS_CHECK
+            {
+                long long top = base;
+                for (int d = 0; d < N; ++d) top += step[d];
+                NINT_ASSERT(base >= 0 && (unsigned long long)top < P.values_len);
+            }
+#endif
             gather_rows<T, N>(P.values + base, step, pol, false, cube);
         }
         // reduce axis 0 first, then 1, ...: v_l * (1 - t) + v_u * t, each op rounded separately
@@ -776,6 +829,7 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
                 off += (long long)idx * P.vstride[d];
             }
         }
+        NINT_ASSERT(off >= 0 && (unsigned long long)off < P.values_len);
         result = ld_table(P.values + off, pol);  // idx <= L-1 on every axis: inside the table even if !ok
         return ok;
     }
@@ -990,6 +1044,7 @@ __global__ void __launch_bounds__(kBlock, 4) interp1d_fused_kernel(const __grid_
         // rcp_div: t by the stored reciprocal with two FMA corrections (one more 8-byte shared load); otherwise by IEEE
         // division (more FP64 instructions, fewer L1 wavefronts).  Both give RN(a / w).
         const bool rcp_div = P.fused_rcp_off != 0u;
+        NINT_ASSERT(k >= 0 && (unsigned)(2 * k + 3) * sizeof(T) < P.fused_bytes);
         T G0, V0, G1, V1, r = T(0);
         ld_rec(pairs + 2 * k, G0, V0);
         ld_rec(pairs + 2 * k + 2, G1, V1);
@@ -1183,6 +1238,7 @@ __global__ void __launch_bounds__(kBlock, slab_ctas(N, (int)sizeof(T))) slab_ker
                 count += __popc(bal);
             }
         }
+        NINT_ASSERT(count <= kSlabSpan);
         __syncwarp();
         // groups of 32: the waiting members first, the rest from the list; the coordinates of the next group
         // are in flight while the current one is evaluated
@@ -1257,6 +1313,7 @@ __global__ void __launch_bounds__(kBlock) pack_cells_kernel(const T* __restrict_
             cell /= nc;
             src += (long long)(l + ((corner >> (ndim - 1 - d)) & 1)) * P.vstride[d];
         }
+        NINT_ASSERT(src >= 0 && (unsigned long long)src < P.values_len);
         out[e] = values[src];
     }
 }

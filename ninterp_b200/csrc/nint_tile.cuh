@@ -45,6 +45,7 @@ struct TileGeom {
     unsigned n_sc;        // superchunks in this launch
     unsigned flags;       // tuning (NINT_TILE_FLAGS): 1 = record stores evict-first, 2 = no evict-first hint on the record
                           // and tile loads, 4 = no evict-last hint on the result stores, 8 = no result stores at all (measurement only), 16 = no prefetch of the result window
+    unsigned long long records_bytes;  // size of `records` (bounds-checked builds)
     unsigned* cursor;     // [n_sc * ntiles] list lengths, kCursorStride apart
     unsigned char* records;  // [n_sc * ntiles][cap] records of kTileRecBytes
 };
@@ -192,8 +193,10 @@ __global__ void __launch_bounds__(kBlock, 4) tile_bin_kernel(const __grid_consta
                                  ((unsigned)(k[2] & ((1 << G.sh[2]) - 1)) << 16);
             const unsigned sc = i >> G.sc_shift;
             const unsigned list = sc * (unsigned)G.ntiles + tile;
+            NINT_ASSERT(sc < G.n_sc && tile < (unsigned)G.ntiles);
             const unsigned slot = atomicAdd(G.cursor + (size_t)list * kCursorStride, 1u);
             if (slot < G.cap) {
+                NINT_ASSERT(record_offset(G, sc, tile, slot) + kTileRecBytes <= G.records_bytes);
                 if (G.flags & 1u) st_record_cs(G.records + record_offset(G, sc, tile, slot), (double)t[0], (double)t[1], (double)t[2], i, loc);
                 else st_record(G.records + record_offset(G, sc, tile, slot), t[0], t[1], t[2], i, loc);
             } else {
@@ -407,6 +410,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
                 for (unsigned slot = base; slot < base + m;) {
                     const unsigned in_page = slot & ((1u << G.page_shift) - 1u);
                     const unsigned len = min((1u << G.page_shift) - in_page, base + m - slot);
+                    NINT_ASSERT(record_offset(G, sc, tile, slot) + (size_t)len * kTileRecBytes <= G.records_bytes);
                     bulk_load(dst + (size_t)(slot - base) * kTileRecBytes, G.records + record_offset(G, sc, tile, slot),
                               len * kTileRecBytes, &rec_full[st], stream_pol);
                     slot += len;
@@ -458,6 +462,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
                 const unsigned long long meta = (unsigned long long)__double_as_longlong(r1.y);
                 const unsigned idx = (unsigned)meta, loc = (unsigned)(meta >> 32);
                 const int off = (int)(loc & 0xffu) * sx + (int)((loc >> 8) & 0xffu) * sy + (int)(loc >> 16);
+                NINT_ASSERT(idx < E.n && (unsigned)(off + sx + sy + 1) * sizeof(T) < G.tile_bytes);
                 const T* c = tile + off;
                 T cube[1 << N];
                 cube[0] = c[0];

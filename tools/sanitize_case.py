@@ -26,6 +26,8 @@ ENABLE, FILL, CLAMP, WRAP, ERROR = 0, 1, 2, 3, 4
 
 
 def axes_of(rng, lens, dtype, uniform=False):
+    if uniform == "analytic":  # nodes are exactly k * h: eligible for the kernels that compute them
+        return [np.arange(L, dtype=dtype) * dtype(0.37) for L in lens]
     return [((np.arange(L) * 0.37 - 1.3) if uniform else (np.cumsum(rng.uniform(0.5, 1.5, L)) + rng.uniform(-3, 3))).astype(dtype) for L in lens]
 
 
@@ -82,7 +84,7 @@ def main():
     run("slab passes nd f32", ND, (17, 5, 4, 3), np.float32, LIN, CLAMP, n, rng, env=dict(forced, NINT_SLABS="2"))
     tile = dict(forced, NINT_ROUTE="tile", NINT_TILE_SC_SHIFT="13", NINT_TILE_SEG_SHIFT="14")
     run("binned tiles", FIXED, (37, 35, 70), np.float64, LIN, ERROR, n, rng, env=tile)
-    run("binned tiles wrap aos", FIXED, (40, 9, 8), np.float64, LIN, WRAP, n, rng, uniform=True, env=tile, aos=True)
+    run("binned tiles wrap aos", FIXED, (40, 9, 8), np.float64, LIN, WRAP, n, rng, uniform="analytic", env=tile, aos=True)
     run("binned tiles f32 nd", ND, (21, 40, 36), np.float32, LIN, FILL, n, rng, env=tile)
     run("length-1 axes nd", ND, (1, 6, 1, 5), np.float64, LIN, CLAMP, n, rng)
     run("length-2 axes", FIXED, (2, 2, 2), np.float64, LIN, ENABLE, n, rng)
@@ -91,6 +93,10 @@ def main():
     run("2d linear", FIXED, (21, 18), np.float32, LIN, WRAP, n, rng)
     run("axis pack beyond shared memory", FIXED, (6000, 5), np.float64, LIN, CLAMP, n, rng)
     run("nd5 f32", ND, (6, 5, 7, 4, 5), np.float32, LIN, WRAP, n, rng)
+    run("nd5 f32 in-range compaction", ND, (6, 5, 7, 4, 5), np.float32, LIN, FILL, 100_000, rng)
+    run("nd4 f64 in-range compaction", ND, (6, 5, 7, 4), np.float64, LIN, ERROR, 100_000, rng)
+    run("1d fused", FIXED, (300,), np.float64, LIN, CLAMP, n, rng)
+    run("analytic", FIXED, (40, 33, 26), np.float64, LIN, CLAMP, n, rng, uniform="analytic", env={"NINT_ANALYTIC": "1"})
     print("sanitize_case: all cases bit-exact against the oracle")
 
 
