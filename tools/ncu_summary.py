@@ -1,11 +1,14 @@
 #!/usr/bin/env python
-"""Prints the headline metrics of an .ncu-rep (via `ncu -i ... --page raw --csv`)."""
+"""Prints the headline metrics of an .ncu-rep (via `ncu -i ... --page raw --csv`).
+usage: ncu_summary.py REPORT [header line ...]   (header lines, e.g. the commit hash, are printed first as comments)"""
 import csv
 import subprocess
 import sys
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors.sum", "lts__t_sector_hit_rate.pct",
+        "lts__t_sectors_srcunit_ltcfabric.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
@@ -33,6 +36,9 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_global_ld.sum"]
 
 rep = sys.argv[1]
+if len(sys.argv) > 2:  # header lines: commit the capture was taken at, the command, ...
+    for line in sys.argv[2:]:
+        print("#", line)
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
