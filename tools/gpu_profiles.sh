@@ -6,8 +6,12 @@ P="python tools/prof_case.py"
 cap() {  # name, kernel regex, count, command...
   local name=$1 regex=$2 count=$3; shift 3
   "$@" > gpurun_out/r2p_plain_$name.log 2>&1 &&
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$regex -c $count -o gpurun_out/r2p_$name "$@" > gpurun_out/r2p_ncu_$name.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$regex -c $count -o /tmp/r2p_$name "$@" > gpurun_out/r2p_ncu_$name.log 2>&1
   echo "$name rc=$?"
+  # the reports are tens of MB each (gpurun brings back at most 64 MiB): summarise here, keep the text
+  python tools/ncu_summary.py /tmp/r2p_$name.ncu-rep "command: $*" > gpurun_out/r2p_summary_$name.txt 2>&1
+  ncu -i /tmp/r2p_$name.ncu-rep --page source --csv > /tmp/r2p_src_$name.csv 2>/dev/null && python tools/ncu_source.py /tmp/r2p_src_$name.csv | awk '!seen[$0]++' > gpurun_out/r2p_source_$name.txt 2>&1
+  rm -f /tmp/r2p_$name.ncu-rep /tmp/r2p_src_$name.csv
 }
 cap slab "slab_kernel" 3 $P --case random --points 1e9 --launches 1
 cap sorted "interp_kernel" 1 $P --case sorted --points 1e9 --launches 1
@@ -21,4 +25,4 @@ cap lin2d "interp_kernel" 1 $P --case 2d --points 1e8 --launches 1
 python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/r2p_bench_plain.log 2>&1 &&
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2p_bench_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/r2p_bench_ncu.log 2>&1
 echo "bench launch list rc=$?"
-ls -la gpurun_out/ | head -40
+du -sh gpurun_out
