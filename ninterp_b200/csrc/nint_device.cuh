@@ -1127,13 +1127,16 @@ constexpr unsigned kSlabSpan = 32u * kSlabPer;  // points a warp scans at a time
 // point evaluation: at 64 registers (4 CTAs) it spills 60-170 bytes per thread and runs at 28.1 Gpoints/s on the
 // headline workload; at 80 registers (3 CTAs, no spills) 32.7; at 96 (2 CTAs) 31.4; at 48 (5 CTAs) 25.6.
 constexpr int slab_ctas(int n, int elem_bytes) { return n <= 3 ? 3 : min_ctas(n, elem_bytes); }
+#ifndef NINT_SLAB_ANA_CTAS
+#define NINT_SLAB_ANA_CTAS 3  // analytic variant (no node records): tried 4
+#endif
 
 // INR (Fill and Error only): one pass over the whole batch in which the members are the points inside the grid on every
 // axis; the others are finished by the scan itself (fill value, or NaN + ExtrapolateError status: n/mod.rs:294-298,
 // 326-337).  With most of a batch out of range (BASELINE config 4: 87 %) the corner gathers then run with full warps
 // instead of four lanes in 32, and nobody calls the out-of-line general path for an out-of-range point.
 template <class T, int N, bool IS_ND, int PRE, bool UNI, bool ANA = false, bool INR = false>
-__global__ void __launch_bounds__(kBlock, slab_ctas(N, (int)sizeof(T))) slab_kernel(const __grid_constant__ Params<T> P) {
+__global__ void __launch_bounds__(kBlock, (ANA && N == 3) ? NINT_SLAB_ANA_CTAS : slab_ctas(N, (int)sizeof(T))) slab_kernel(const __grid_constant__ Params<T> P) {
     extern __shared__ __align__(16) unsigned char smem_pack[];
     __shared__ unsigned short s_list[kBlock / 32][kSlabSpan];
     __shared__ unsigned long long s_info[4];  // n_error, n_panic, first_error, first_panic
