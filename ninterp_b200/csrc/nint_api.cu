@@ -842,6 +842,32 @@ int launch_tiles(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
     return rc;
 }
 
+// The single pass over a launch's points: the TMA-pipelined kernel for the whole chunks when it applies (hard-coded
+// 2-D/3-D Linear or Nearest, axis pack staged in shared memory, struct-of-arrays columns on 16-byte boundaries, batch
+// large enough), interp_kernel for the rest.  `coherent` = the launch is gated on the order probe's coherent verdict.
+template <class T>
+cudaError_t launch_single_pass(const nint_handle* h, nint::Params<T> P, nint::LaunchCfg cfg, bool use_pipe) {
+    const bool eligible = use_pipe && !cfg.is_nd && (cfg.ndim == 2 || cfg.ndim == 3) && h->smem_axes && P.coord_stride == 1 &&
+                          (cfg.strategy == NINT_LINEAR || cfg.strategy == NINT_NEAREST) && P.n >= (1ull << 20);
+    bool aligned = true;
+    for (int d = 0; d < cfg.ndim; ++d) aligned = aligned && (((uintptr_t)P.coords[d]) & 15u) == 0;
+    if (!(eligible && aligned)) return nint::launch_fixed<T>(P, cfg);
+    const unsigned long long whole = P.n / nint::kPipeChunk * nint::kPipeChunk;
+    cfg.pipe = 1;
+    const unsigned long long n = P.n;
+    P.n = whole;
+    cudaError_t e = nint::launch_fixed<T>(P, cfg);
+    if (e != cudaSuccess || whole == n) return e;
+    cfg.pipe = 0;  // the ragged tail
+    for (int d = 0; d < cfg.ndim; ++d) P.coords[d] += whole;
+    P.out += whole;
+    if (P.status) P.status += whole;
+    P.index_base += whole;
+    P.n = n - whole;
+    P.blocked = 0;
+    return nint::launch_fixed<T>(P, cfg);
+}
+
 template <class T>
 int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride, size_t n, void* out,
                  uint8_t* status, nint_batch_info* info_dev, unsigned long long index_base, cudaStream_t stream,
@@ -887,7 +913,11 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     cfg.sm_count = h->sm_count;
     cfg.stream = stream;
     cfg.slab = 0;
+    cfg.pipe = 0;
     cfg.inrange = 0;
+    // NINT_PIPE: 0 = never, 1 = every single pass that qualifies, unset = the single pass of coherent batches
+    const char* e_pipe = std::getenv("NINT_PIPE");
+    const int pipe_mode = e_pipe ? std::atoi(e_pipe) : -1;
     // Chunks of the host pipeline are bound by the PCIe copies around them (a 4 Mi-point chunk is ~2.3 ms of copies
     // against 0.2 ms of single pass): no order probe, no multi-launch routes there.
     int windows = pipeline_chunk ? 0 : slab_windows(h, n);
@@ -909,7 +939,7 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     }
     if (windows <= 0 && !tile) {
         h->last_mode.store(nullptr, std::memory_order_relaxed);
-        cudaError_t e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : nint::launch_fixed<T>(P, cfg);
+        cudaError_t e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : launch_single_pass<T>(h, P, cfg, pipe_mode == 1);
         if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
         return NINT_OK;
     }
@@ -925,7 +955,7 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     P.mode_flag = flag;
     P.mode_want = nint::kModeCoherent;
     P.blocked = std::getenv("NINT_NO_BLOCKED") ? 0 : 1;
-    e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : nint::launch_fixed<T>(P, cfg);
+    e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : launch_single_pass<T>(h, P, cfg, pipe_mode != 0);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     P.blocked = 0;
     P.mode_want = nint::kModeRandom;

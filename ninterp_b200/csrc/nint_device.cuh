@@ -52,6 +52,10 @@ constexpr int kMaxDim = NINT_MAX_NDIM;
 #define NINT_BLOCK 256
 #endif
 constexpr int kBlock = NINT_BLOCK;
+// interp_pipe_kernel (nint_pipe.cuh)
+constexpr int kPipeChunk = 512;    // points per stage = consumer threads
+constexpr int kPipeStages = 4;
+constexpr int kPipeThreads = kPipeChunk + 32;  // + the producer warp
 // The point loop indexes with 32 bits (fewer registers, one-instruction address arithmetic).
 constexpr unsigned long long kMaxLaunchPoints = 1ull << 30;
 
@@ -1330,6 +1334,7 @@ struct LaunchCfg {
     int all_uniform;  // every axis is uniform and fast-path eligible
     int all_analytic; // ... and its nodes are exactly g0 + k * h (launch the single-pass kernels that compute them)
     int slab_analytic; // the same for the slab passes
+    int pipe;         // launch interp_pipe_kernel (whole chunks of the batch; hard-coded 2-D/3-D, axes in shared memory)
     int slab;         // launch slab_kernel (Params::win_*) instead of interp_kernel
     int inrange;      // ... in its one-pass form whose members are the in-range points (Fill, Error)
     unsigned smem_bytes;

@@ -25,6 +25,11 @@ cudaError_t dispatch_strategy(const Params<T>& P, const LaunchCfg& cfg) {
 
 template <>
 cudaError_t launch_fixed<NINT_T>(const Params<NINT_T>& P, const LaunchCfg& cfg) {
+    if (cfg.pipe) {  // pipelined single pass: Interp2D / Interp3D, Linear and Nearest
+        if (cfg.ndim == 3) return cfg.strategy == NINT_LINEAR ? launch_pipe<NINT_T, 3, false, NINT_LINEAR>(P, cfg) : launch_pipe<NINT_T, 3, false, NINT_NEAREST>(P, cfg);
+        if (cfg.ndim == 2) return cfg.strategy == NINT_LINEAR ? launch_pipe<NINT_T, 2, false, NINT_LINEAR>(P, cfg) : launch_pipe<NINT_T, 2, false, NINT_NEAREST>(P, cfg);
+        return cudaErrorInvalidValue;
+    }
     if (cfg.slab) {
         switch (cfg.ndim) {
         case 1: return launch_slab<NINT_T, 1, false>(P, cfg);

@@ -3,6 +3,7 @@
 #include <atomic>
 
 #include "nint_device.cuh"
+#include "nint_pipe.cuh"
 
 namespace nint {
 
@@ -34,6 +35,46 @@ cudaError_t launch_variant(const Params<T>& P, const LaunchCfg& cfg) {
     kern<<<grid, kBlock, smem, (cudaStream_t)cfg.stream>>>(P);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
+}
+
+// The pipelined form of the single pass (nint_pipe.cuh) for the whole chunks of a batch; false when it does not
+// apply (then nothing was launched).  The caller runs interp_kernel on the remaining points.
+template <class T, int N, bool IS_ND, int STRAT, int PRE, bool UNI>
+cudaError_t launch_pipe_variant(const Params<T>& P, const LaunchCfg& cfg) {
+    auto kern = interp_pipe_kernel<T, N, IS_ND, STRAT, PRE, UNI>;
+    const unsigned smem = (unsigned)(kPipeStages * N * kPipeChunk * sizeof(T)) + cfg.smem_bytes;
+    static thread_local unsigned configured = 0;
+    if (configured < smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    static thread_local unsigned cached_smem = ~0u;
+    static thread_local int cached_bps = 0;
+    int bps = cached_bps;
+    if (cached_smem != smem || bps == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kPipeThreads, smem);
+        if (e != cudaSuccess) return e;
+        if (bps < 1) bps = 1;
+        cached_bps = bps;
+        cached_smem = smem;
+    }
+    const unsigned long long chunks = P.n / kPipeChunk;
+    const unsigned long long cap = (unsigned long long)cfg.sm_count * (unsigned long long)bps;
+    const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
+    if (grid == 0) return cudaSuccess;
+    kern<<<grid, kPipeThreads, smem, (cudaStream_t)cfg.stream>>>(P);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+template <class T, int N, bool IS_ND, int STRAT>
+cudaError_t launch_pipe(const Params<T>& P, const LaunchCfg& cfg) {
+    const bool uni = cfg.all_uniform && (STRAT != NINT_LINEAR || P.cells != nullptr);
+    if (P.extrap == NINT_EXTRAPOLATE_CLAMP)
+        return uni ? launch_pipe_variant<T, N, IS_ND, STRAT, kPreClamp, true>(P, cfg) : launch_pipe_variant<T, N, IS_ND, STRAT, kPreClamp, false>(P, cfg);
+    if (P.extrap == NINT_EXTRAPOLATE_WRAP)
+        return uni ? launch_pipe_variant<T, N, IS_ND, STRAT, kPreWrap, true>(P, cfg) : launch_pipe_variant<T, N, IS_ND, STRAT, kPreWrap, false>(P, cfg);
+    return uni ? launch_pipe_variant<T, N, IS_ND, STRAT, kPrePlain, true>(P, cfg) : launch_pipe_variant<T, N, IS_ND, STRAT, kPrePlain, false>(P, cfg);
 }
 
 // Clamp and Wrap enter the fast path (clamp first / wrap and retry), so they select their own kernels; so do

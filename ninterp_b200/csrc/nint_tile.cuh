@@ -21,6 +21,7 @@
 #pragma once
 #include <cuda.h>
 
+#include "nint_async.cuh"
 #include "nint_device.cuh"
 
 namespace nint {
@@ -257,33 +258,6 @@ __global__ void __launch_bounds__(kBlock, 4) tile_bin_kernel(const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // Evaluate: TMA-staged tiles, records blended from shared memory.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Waits for the phase with the given parity.  try_wait suspends the thread for a hardware-bounded time per attempt; the
-// attempt count is bounded too, so that a descriptor the hardware rejects ends in a trap rather than a hung GPU.
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    const unsigned addr = smem_u32(bar);
-    for (unsigned tries = 0; tries < (1u << 24); ++tries) {
-        unsigned done;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) return;
-    }
-    __trap();
-}
 // One tile: box (box[2], box[1], box[0]) of the table at element coordinates (c0 innermost) -> shared memory.
 __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1,
                                               int c2, unsigned long long pol) {
@@ -292,34 +266,6 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map,
             smem_u32(dst)),
         "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(pol)
         : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// Contiguous global -> shared copy by the TMA engine (UBLKCP); size and both addresses are multiples of 16.
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar,
-                                          unsigned long long pol) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
-                 : "memory");
-}
-__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void st_hint(double* p, double v, unsigned long long pol) {
-    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void st_hint(float* p, float v, unsigned long long pol) {
-    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
 }
 
 template <class T>

@@ -317,6 +317,37 @@ def test_slab_passes_and_order_probe(monkeypatch):
     assert _lib.lib().nint_last_query_order(g._h) == 0
 
 
+def test_pipelined_single_pass(monkeypatch):
+    # the TMA-pipelined form of the single pass (nint_pipe.cuh): coordinates arrive in shared memory by cp.async.bulk,
+    # whole chunks of 512 points; the ragged tail and unaligned / array-of-points inputs go to interp_kernel
+    import torch
+
+    from gpu_util import assert_same, expected_info, gpu_eval, make_pair
+
+    monkeypatch.setenv("NINT_PIPE", "1")
+    rng = np.random.default_rng(616)
+    n = 1_100_003
+    for kind, lens, dtype, mode in [(FIXED, (40, 33, 26), np.float64, "nonuniform"), (FIXED, (57, 31), np.float64, "uniform"),
+                                    (FIXED, (19, 22, 35), np.float32, "uniform"), (FIXED, (64, 48), np.float32, "nonuniform")]:
+        axes = _axes(rng, lens, dtype, mode)
+        values = rng.uniform(-1, 1, lens).astype(dtype)
+        cols = _queries(rng, axes, n, dtype, 0.1)
+        for strat, extrap in [(LIN, e) for e in (ERROR, CLAMP, ENABLE, FILL, WRAP)] + [(NEA, e) for e in (ERROR, CLAMP, WRAP)]:
+            g, o = make_pair(kind, axes, values, strat, extrap, fill=0.5, dtype=dtype)
+            want, st_want = o.eval(cols, nthreads=O.max_threads())
+            got, st, info = gpu_eval(g, cols)
+            assert_same(got, st, want, st_want, f"pipe {lens} {dtype.__name__} {strat} {extrap}")
+            assert info == expected_info(st_want)
+        # columns that start 8 bytes off a 16-byte boundary: not eligible, same results
+        g, o = make_pair(kind, axes, values, LIN, CLAMP, dtype=dtype)
+        dev = torch.device("cuda", g.device)
+        shifted = [torch.from_numpy(np.concatenate([c[:1], c])).to(dev)[1:] for c in cols]
+        out = g.interpolate_batch(shifted)
+        torch.cuda.synchronize()
+        want, _ = o.eval(cols, nthreads=O.max_threads())
+        assert np.array_equal(out.cpu().numpy().view(np.uint8), want.view(np.uint8))
+
+
 def test_inrange_compaction_pass():
     # InterpND with four or more axes under Fill / Error: the scan finishes the out-of-range points itself and the
     # in-range ones are compacted into full warps before their 2^N corners are gathered (slab_kernel<INR>)
