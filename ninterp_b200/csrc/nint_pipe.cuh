@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) interp_pipe_kernel(const __gr
     if (tid == 0) {
         for (int s = 0; s < kPipeStages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kPipeChunk / 32);
+            mbar_init(&empty[s], kPipeChunk / 32 + 1);  // the consumer warps and the prefetch warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -46,7 +46,44 @@ __global__ void __launch_bounds__(kPipeThreads, 2) interp_pipe_kernel(const __gr
     const unsigned per = (nchunks + gridDim.x - 1) / gridDim.x;
     const unsigned c_lo = min(nchunks, blockIdx.x * per), c_hi = min(nchunks, c_lo + per);
 
-    if (tid >= (unsigned)kPipeChunk) {
+    if (tid >= (unsigned)kPipeChunk + 32u) {
+        // ---------------------------------------------------------------- table prefetch (one warp)
+        // On a cell-ordered batch nearly every trip of a consumer warp meets a cell nobody has touched yet, and the
+        // warp then waits a DRAM round trip for its corner block: with 32 warps per SM that alone caps the kernel at
+        // ~145 Gpoints/s (32 warps x 32 points per microsecond and SM).  This warp reads the coordinates of a chunk as
+        // soon as they land -- the consumers are a few chunks behind -- guesses the cell of every kPipeSample-th point
+        // and asks for its line.  A hint only: wrong guesses (non-uniform axes, out-of-range points) cost nothing but
+        // the request.
+        const unsigned lane = tid & 31u;
+        unsigned st = 0, phase = 0;
+        for (unsigned c = c_lo; c < c_hi; ++c) {
+            mbar_wait(&full[st], phase);
+            if (STRAT == NINT_LINEAR && UNI && P.cells != nullptr && P.prefetch) {
+                unsigned last = ~0u;
+                for (unsigned j = lane * (kPipeChunk / 32); j < (lane + 1) * (kPipeChunk / 32); j += kPipeSample) {
+                    unsigned cell = 0;
+#pragma unroll
+                    for (int d = 0; d < N; ++d) {
+                        const T x = stage0[((size_t)st * N + d) * kPipeChunk + j];
+                        int k = to_int_sat((x - P.g0[d]) * P.inv_h[d]);
+                        k = max(0, min(k, P.L[d] - 2));
+                        cell += (unsigned)k * (unsigned)P.cstride[d];
+                    }
+                    if (cell != last) {
+                        if (P.prefetch == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.cells + (size_t)cell * (1 << N)));
+                        else asm volatile("prefetch.global.L2 [%0];" ::"l"(P.cells + (size_t)cell * (1 << N)));
+                    }
+                    last = cell;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+            if (++st == kPipeStages) {
+                st = 0;
+                phase ^= 1u;
+            }
+        }
+    } else if (tid >= (unsigned)kPipeChunk) {
         // ---------------------------------------------------------------- producer (one lane)
         if (tid == (unsigned)kPipeChunk) {
             const unsigned long long pol = l2_policy_evict_first();  // the query stream is touched once
