@@ -93,7 +93,7 @@ struct Params {
     const int* mode_flag;
     int mode_want;
     int blocked;  // interp_kernel: every CTA walks one contiguous range of the batch instead of striding over it
-    int prefetch; // interp_pipe_kernel: 0 = no table prefetch, 1 = into L2, 2 = into L1 (NINT_PIPE_PREFETCH)
+    int prefetch; // interp_pipe_kernel: 0 = no table prefetch, 1 = TMA copies into L2, 2 = prefetch.L2, 3 = prefetch.L1 (NINT_PIPE_PREFETCH)
     T win_lo_x, win_hi_x;
     int win_first, win_last;
     int L[kMaxDim];

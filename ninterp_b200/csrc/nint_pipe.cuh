@@ -18,7 +18,8 @@ namespace nint {
 template <class T, int N, bool IS_ND, int STRAT, int PRE, bool UNI>
 __global__ void __launch_bounds__(kPipeThreads, 2) interp_pipe_kernel(const __grid_constant__ Params<T> P) {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
-    __shared__ __align__(8) unsigned long long full[kPipeStages], empty[kPipeStages];
+    __shared__ __align__(8) unsigned long long full[kPipeStages], empty[kPipeStages], pf_bar;
+    __shared__ __align__(128) double pf_slot[32 * (kPipeChunk / 32 / kPipeSample) * 16];  // scratch the prefetch warp's bulk copies land in (never read)
     __shared__ unsigned long long s_info[4];  // n_error, n_panic, first_error, first_panic
     if (P.mode_flag != nullptr && *P.mode_flag != P.mode_want) return;  // the other query-order mode runs this batch
     // dynamic shared memory: kPipeStages x N columns of kPipeChunk coordinates, then the axis pack
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) interp_pipe_kernel(const __gr
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kPipeChunk / 32 + 1);  // the consumer warps and the prefetch warp
         }
+        mbar_init(&pf_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -55,12 +57,20 @@ __global__ void __launch_bounds__(kPipeThreads, 2) interp_pipe_kernel(const __gr
         // and asks for its line.  A hint only: wrong guesses (non-uniform axes, out-of-range points) cost nothing but
         // the request.
         const unsigned lane = tid & 31u;
-        unsigned st = 0, phase = 0;
+        constexpr int kPer = kPipeChunk / 32 / kPipeSample;  // sampled points per lane and chunk
+        constexpr unsigned kCellBytes = (unsigned)((1 << N) * sizeof(T));
+        const bool active = STRAT == NINT_LINEAR && UNI && P.cells != nullptr && P.prefetch != 0;
+        const unsigned long long pf_pol = l2_policy_evict_first();
+        unsigned st = 0, phase = 0, pf_phase = 0;
+        bool armed = false;  // a phase of pf_bar is open: bulk copies of the previous chunk may still be landing
         for (unsigned c = c_lo; c < c_hi; ++c) {
             mbar_wait(&full[st], phase);
-            if (STRAT == NINT_LINEAR && UNI && P.cells != nullptr && P.prefetch) {
-                unsigned last = ~0u;
-                for (unsigned j = lane * (kPipeChunk / 32); j < (lane + 1) * (kPipeChunk / 32); j += kPipeSample) {
+            if (active) {
+                unsigned cells[kPer];
+                unsigned want = 0, last = ~0u;
+#pragma unroll
+                for (int s = 0; s < kPer; ++s) {
+                    const unsigned j = lane * (kPipeChunk / 32) + s * kPipeSample;
                     unsigned cell = 0;
 #pragma unroll
                     for (int d = 0; d < N; ++d) {
@@ -69,11 +79,36 @@ __global__ void __launch_bounds__(kPipeThreads, 2) interp_pipe_kernel(const __gr
                         k = max(0, min(k, P.L[d] - 2));
                         cell += (unsigned)k * (unsigned)P.cstride[d];
                     }
-                    if (cell != last) {
-                        if (P.prefetch == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.cells + (size_t)cell * (1 << N)));
-                        else asm volatile("prefetch.global.L2 [%0];" ::"l"(P.cells + (size_t)cell * (1 << N)));
-                    }
+                    cells[s] = cell;
+                    if (cell != last) want |= 1u << s;
                     last = cell;
+                }
+                if (P.prefetch == 1) {
+                    // Through the TMA engine: bulk copies of the cells into scratch slots nobody reads.  The lines land
+                    // in L2, and translation misses on the 1 GiB table are the copy engine's to wait for, not the
+                    // load/store unit's (prefetch.global stalls it: 143 -> 115 Gpoints/s).  One mbarrier phase per
+                    // chunk, so that the CTA can wait for the last copies before it exits.
+                    const unsigned total = __reduce_add_sync(0xffffffffu, (unsigned)__popc(want));
+                    if (armed) {
+                        mbar_wait(&pf_bar, pf_phase);
+                        pf_phase ^= 1u;
+                    }
+                    armed = total != 0u;
+                    if (armed) {
+                        if (lane == 0) mbar_expect_tx(&pf_bar, total * kCellBytes);
+                        __syncwarp();
+#pragma unroll
+                        for (int s = 0; s < kPer; ++s)
+                            if (want & (1u << s))
+                                bulk_load(pf_slot + (lane * kPer + s) * 16, P.cells + (size_t)cells[s] * (1 << N), kCellBytes, &pf_bar, pf_pol);
+                    }
+                } else {
+#pragma unroll
+                    for (int s = 0; s < kPer; ++s)
+                        if (want & (1u << s)) {
+                            if (P.prefetch == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.cells + (size_t)cells[s] * (1 << N)));
+                            else asm volatile("prefetch.global.L1 [%0];" ::"l"(P.cells + (size_t)cells[s] * (1 << N)));
+                        }
                 }
             }
             __syncwarp();
@@ -83,6 +118,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) interp_pipe_kernel(const __gr
                 phase ^= 1u;
             }
         }
+        if (armed) mbar_wait(&pf_bar, pf_phase);  // no copy may land in this CTA's shared memory after it has gone
     } else if (tid >= (unsigned)kPipeChunk) {
         // ---------------------------------------------------------------- producer (one lane)
         if (tid == (unsigned)kPipeChunk) {
