@@ -854,10 +854,6 @@ cudaError_t launch_single_pass(const nint_handle* h, nint::Params<T> P, nint::La
     if (!(eligible && aligned)) return nint::launch_fixed<T>(P, cfg);
     const unsigned long long whole = P.n / nint::kPipeChunk * nint::kPipeChunk;
     cfg.pipe = 1;
-    {
-        const char* env = std::getenv("NINT_PIPE_PREFETCH");
-        P.prefetch = env ? std::atoi(env) : 1;
-    }
     const unsigned long long n = P.n;
     P.n = whole;
     cudaError_t e = nint::launch_fixed<T>(P, cfg);

@@ -55,8 +55,7 @@ constexpr int kBlock = NINT_BLOCK;
 // interp_pipe_kernel (nint_pipe.cuh)
 constexpr int kPipeChunk = 512;    // points per stage = consumer threads
 constexpr int kPipeStages = 4;
-constexpr int kPipeThreads = kPipeChunk + 64;  // + the producer warp and the table-prefetch warp
-constexpr int kPipeSample = 4;     // the prefetch warp looks at every kPipeSample-th point of a chunk
+constexpr int kPipeThreads = kPipeChunk + 32;  // + the producer warp
 // The point loop indexes with 32 bits (fewer registers, one-instruction address arithmetic).
 constexpr unsigned long long kMaxLaunchPoints = 1ull << 30;
 
@@ -93,7 +92,6 @@ struct Params {
     const int* mode_flag;
     int mode_want;
     int blocked;  // interp_kernel: every CTA walks one contiguous range of the batch instead of striding over it
-    int prefetch; // interp_pipe_kernel: 0 = no table prefetch, 1 = TMA copies into L2, 2 = prefetch.L2, 3 = prefetch.L1 (NINT_PIPE_PREFETCH)
     T win_lo_x, win_hi_x;
     int win_first, win_last;
     int L[kMaxDim];

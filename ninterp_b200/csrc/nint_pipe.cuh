@@ -7,7 +7,15 @@
 // kPipeStages chunks of kPipeChunk points in flight with cp.async.bulk (UBLKCP, one copy per coordinate column and
 // chunk, mbarrier transaction counts); the consumer warps read their coordinates from shared memory, release the
 // stage at once and evaluate the point exactly as interp_kernel does (same fast_point / general_point, same stores).
-// Every CTA walks one contiguous range of chunks.  Struct-of-arrays input with 16-byte aligned columns only; the
+// Every CTA walks one contiguous range of chunks.
+//
+// Measured on B200 (1e9 points, 256^3 f64): cell-ordered 143 -> 146 Gpoints/s, Morton order 144 -> 151, queries grouped
+// by 8^3-cell tiles 84 -> 89, f32 cell-ordered 178 -> 187.  The gain is small because the wait moves: with the
+// coordinates on time a warp still meets, on nearly every trip, a cell nobody has touched yet and waits a DRAM round
+// trip for its corner block (32 warps x 32 points per ~1 us and SM = 145 Gpoints/s).  Tried against that and dropped:
+// a 17th warp that guesses the cells of the chunks in flight and requests their lines -- with prefetch.global the
+// load/store unit stalls on the translation misses of the 1 GiB table (143 -> 115 Gpoints/s), with cp.async.bulk
+// copies into a scratch slot the requests are off the LSU but the warp's own round trip gates the stage ring (68).  Struct-of-arrays input with 16-byte aligned columns only; the
 // last n % kPipeChunk points and every other case go to interp_kernel.
 #pragma once
 #include "nint_async.cuh"
@@ -18,8 +26,7 @@ namespace nint {
 template <class T, int N, bool IS_ND, int STRAT, int PRE, bool UNI>
 __global__ void __launch_bounds__(kPipeThreads, 2) interp_pipe_kernel(const __grid_constant__ Params<T> P) {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
-    __shared__ __align__(8) unsigned long long full[kPipeStages], empty[kPipeStages], pf_bar;
-    __shared__ __align__(128) double pf_slot[32 * (kPipeChunk / 32 / kPipeSample) * 16];  // scratch the prefetch warp's bulk copies land in (never read)
+    __shared__ __align__(8) unsigned long long full[kPipeStages], empty[kPipeStages];
     __shared__ unsigned long long s_info[4];  // n_error, n_panic, first_error, first_panic
     if (P.mode_flag != nullptr && *P.mode_flag != P.mode_want) return;  // the other query-order mode runs this batch
     // dynamic shared memory: kPipeStages x N columns of kPipeChunk coordinates, then the axis pack
@@ -36,9 +43,8 @@ __global__ void __launch_bounds__(kPipeThreads, 2) interp_pipe_kernel(const __gr
     if (tid == 0) {
         for (int s = 0; s < kPipeStages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kPipeChunk / 32 + 1);  // the consumer warps and the prefetch warp
+            mbar_init(&empty[s], kPipeChunk / 32);
         }
-        mbar_init(&pf_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -48,78 +54,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) interp_pipe_kernel(const __gr
     const unsigned per = (nchunks + gridDim.x - 1) / gridDim.x;
     const unsigned c_lo = min(nchunks, blockIdx.x * per), c_hi = min(nchunks, c_lo + per);
 
-    if (tid >= (unsigned)kPipeChunk + 32u) {
-        // ---------------------------------------------------------------- table prefetch (one warp)
-        // On a cell-ordered batch nearly every trip of a consumer warp meets a cell nobody has touched yet, and the
-        // warp then waits a DRAM round trip for its corner block: with 32 warps per SM that alone caps the kernel at
-        // ~145 Gpoints/s (32 warps x 32 points per microsecond and SM).  This warp reads the coordinates of a chunk as
-        // soon as they land -- the consumers are a few chunks behind -- guesses the cell of every kPipeSample-th point
-        // and asks for its line.  A hint only: wrong guesses (non-uniform axes, out-of-range points) cost nothing but
-        // the request.
-        const unsigned lane = tid & 31u;
-        constexpr int kPer = kPipeChunk / 32 / kPipeSample;  // sampled points per lane and chunk
-        constexpr unsigned kCellBytes = (unsigned)((1 << N) * sizeof(T));
-        const bool active = STRAT == NINT_LINEAR && UNI && P.cells != nullptr && P.prefetch != 0;
-        const unsigned long long pf_pol = l2_policy_evict_first();
-        unsigned st = 0, phase = 0, pf_phase = 0;
-        bool armed = false;  // a phase of pf_bar is open: bulk copies of the previous chunk may still be landing
-        for (unsigned c = c_lo; c < c_hi; ++c) {
-            mbar_wait(&full[st], phase);
-            if (active) {
-                unsigned cells[kPer];
-                unsigned want = 0, last = ~0u;
-#pragma unroll
-                for (int s = 0; s < kPer; ++s) {
-                    const unsigned j = lane * (kPipeChunk / 32) + s * kPipeSample;
-                    unsigned cell = 0;
-#pragma unroll
-                    for (int d = 0; d < N; ++d) {
-                        const T x = stage0[((size_t)st * N + d) * kPipeChunk + j];
-                        int k = to_int_sat((x - P.g0[d]) * P.inv_h[d]);
-                        k = max(0, min(k, P.L[d] - 2));
-                        cell += (unsigned)k * (unsigned)P.cstride[d];
-                    }
-                    cells[s] = cell;
-                    if (cell != last) want |= 1u << s;
-                    last = cell;
-                }
-                if (P.prefetch == 1) {
-                    // Through the TMA engine: bulk copies of the cells into scratch slots nobody reads.  The lines land
-                    // in L2, and translation misses on the 1 GiB table are the copy engine's to wait for, not the
-                    // load/store unit's (prefetch.global stalls it: 143 -> 115 Gpoints/s).  One mbarrier phase per
-                    // chunk, so that the CTA can wait for the last copies before it exits.
-                    const unsigned total = __reduce_add_sync(0xffffffffu, (unsigned)__popc(want));
-                    if (armed) {
-                        mbar_wait(&pf_bar, pf_phase);
-                        pf_phase ^= 1u;
-                    }
-                    armed = total != 0u;
-                    if (armed) {
-                        if (lane == 0) mbar_expect_tx(&pf_bar, total * kCellBytes);
-                        __syncwarp();
-#pragma unroll
-                        for (int s = 0; s < kPer; ++s)
-                            if (want & (1u << s))
-                                bulk_load(pf_slot + (lane * kPer + s) * 16, P.cells + (size_t)cells[s] * (1 << N), kCellBytes, &pf_bar, pf_pol);
-                    }
-                } else {
-#pragma unroll
-                    for (int s = 0; s < kPer; ++s)
-                        if (want & (1u << s)) {
-                            if (P.prefetch == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.cells + (size_t)cells[s] * (1 << N)));
-                            else asm volatile("prefetch.global.L1 [%0];" ::"l"(P.cells + (size_t)cells[s] * (1 << N)));
-                        }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[st]);
-            if (++st == kPipeStages) {
-                st = 0;
-                phase ^= 1u;
-            }
-        }
-        if (armed) mbar_wait(&pf_bar, pf_phase);  // no copy may land in this CTA's shared memory after it has gone
-    } else if (tid >= (unsigned)kPipeChunk) {
+    if (tid >= (unsigned)kPipeChunk) {
         // ---------------------------------------------------------------- producer (one lane)
         if (tid == (unsigned)kPipeChunk) {
             const unsigned long long pol = l2_policy_evict_first();  // the query stream is touched once
