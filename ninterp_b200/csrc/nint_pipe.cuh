@@ -15,7 +15,8 @@
 // trip for its corner block (32 warps x 32 points per ~1 us and SM = 145 Gpoints/s).  Tried against that and dropped:
 // a 17th warp that guesses the cells of the chunks in flight and requests their lines -- with prefetch.global the
 // load/store unit stalls on the translation misses of the 1 GiB table (143 -> 115 Gpoints/s), with cp.async.bulk
-// copies into a scratch slot the requests are off the LSU but the warp's own round trip gates the stage ring (68).  Struct-of-arrays input with 16-byte aligned columns only; the
+// copies into a scratch slot the requests are off the LSU but the warp's own round trip gates the stage ring (68); and the same guess made by
+// warp 0 of the consumers two chunks ahead, non-blocking, one point in sixteen (146 -> 138, L1 or L2 alike).  Struct-of-arrays input with 16-byte aligned columns only; the
 // last n % kPipeChunk points and every other case go to interp_kernel.
 #pragma once
 #include "nint_async.cuh"
