@@ -854,10 +854,6 @@ cudaError_t launch_single_pass(const nint_handle* h, nint::Params<T> P, nint::La
     if (!(eligible && aligned)) return nint::launch_fixed<T>(P, cfg);
     const unsigned long long whole = P.n / nint::kPipeChunk * nint::kPipeChunk;
     cfg.pipe = 1;
-    {
-        const char* env = std::getenv("NINT_PIPE_PREFETCH");
-        cfg.pipe_prefetch = env ? std::atoi(env) : 0;
-    }
     const unsigned long long n = P.n;
     P.n = whole;
     cudaError_t e = nint::launch_fixed<T>(P, cfg);
@@ -918,7 +914,6 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     cfg.stream = stream;
     cfg.slab = 0;
     cfg.pipe = 0;
-    cfg.pipe_prefetch = 0;
     cfg.inrange = 0;
     // NINT_PIPE: 0 = never, 1 = every single pass that qualifies, unset = the single pass of coherent batches
     const char* e_pipe = std::getenv("NINT_PIPE");

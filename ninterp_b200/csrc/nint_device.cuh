@@ -1334,7 +1334,6 @@ struct LaunchCfg {
     int all_uniform;  // every axis is uniform and fast-path eligible
     int all_analytic; // ... and its nodes are exactly g0 + k * h (launch the single-pass kernels that compute them)
     int slab_analytic; // the same for the slab passes
-    int pipe_prefetch; // interp_pipe_kernel: warp 0 requests the table lines two chunks ahead (1 = L2, 2 = L1)
     int pipe;         // launch interp_pipe_kernel (whole chunks of the batch; hard-coded 2-D/3-D, axes in shared memory)
     int slab;         // launch slab_kernel (Params::win_*) instead of interp_kernel
     int inrange;      // ... in its one-pass form whose members are the in-range points (Fill, Error)

@@ -39,9 +39,9 @@ cudaError_t launch_variant(const Params<T>& P, const LaunchCfg& cfg) {
 
 // The pipelined form of the single pass (nint_pipe.cuh) for the whole chunks of a batch; false when it does not
 // apply (then nothing was launched).  The caller runs interp_kernel on the remaining points.
-template <class T, int N, bool IS_ND, int STRAT, int PRE, bool UNI, int PF = 0>
+template <class T, int N, bool IS_ND, int STRAT, int PRE, bool UNI>
 cudaError_t launch_pipe_variant(const Params<T>& P, const LaunchCfg& cfg) {
-    auto kern = interp_pipe_kernel<T, N, IS_ND, STRAT, PRE, UNI, PF>;
+    auto kern = interp_pipe_kernel<T, N, IS_ND, STRAT, PRE, UNI>;
     const unsigned smem = (unsigned)(kPipeStages * N * kPipeChunk * sizeof(T)) + cfg.smem_bytes;
     static thread_local unsigned configured = 0;
     if (configured < smem) {
@@ -70,11 +70,6 @@ cudaError_t launch_pipe_variant(const Params<T>& P, const LaunchCfg& cfg) {
 template <class T, int N, bool IS_ND, int STRAT>
 cudaError_t launch_pipe(const Params<T>& P, const LaunchCfg& cfg) {
     const bool uni = cfg.all_uniform && (STRAT != NINT_LINEAR || P.cells != nullptr);
-    if constexpr (STRAT == NINT_LINEAR && N == 3) {  // table prefetch by warp 0 (experiment: NINT_PIPE_PREFETCH=1|2)
-        if (uni && cfg.pipe_prefetch && P.extrap != NINT_EXTRAPOLATE_CLAMP && P.extrap != NINT_EXTRAPOLATE_WRAP && P.cells != nullptr)
-            return cfg.pipe_prefetch == 1 ? launch_pipe_variant<T, N, IS_ND, STRAT, kPrePlain, true, 1>(P, cfg)
-                                          : launch_pipe_variant<T, N, IS_ND, STRAT, kPrePlain, true, 2>(P, cfg);
-    }
     if (P.extrap == NINT_EXTRAPOLATE_CLAMP)
         return uni ? launch_pipe_variant<T, N, IS_ND, STRAT, kPreClamp, true>(P, cfg) : launch_pipe_variant<T, N, IS_ND, STRAT, kPreClamp, false>(P, cfg);
     if (P.extrap == NINT_EXTRAPOLATE_WRAP)

@@ -24,7 +24,7 @@
 
 namespace nint {
 
-template <class T, int N, bool IS_ND, int STRAT, int PRE, bool UNI, int PF = 0>
+template <class T, int N, bool IS_ND, int STRAT, int PRE, bool UNI>
 __global__ void __launch_bounds__(kPipeThreads, 2) interp_pipe_kernel(const __grid_constant__ Params<T> P) {
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     __shared__ __align__(8) unsigned long long full[kPipeStages], empty[kPipeStages];
@@ -90,32 +90,6 @@ __global__ void __launch_bounds__(kPipeThreads, 2) interp_pipe_kernel(const __gr
                 phase ^= 1u;
             }
             const unsigned i = c * kPipeChunk + tid;
-            if (PF != 0 && tid < 32u && c + 2u < c_hi) {
-                // Warp 0 looks two chunks ahead: if that chunk's coordinates have landed (non-blocking test), each lane
-                // guesses the cell of one point in sixteen and asks for its corner block.  A hint: a wrong guess costs
-                // a request, a chunk that has not landed is skipped.
-                const unsigned k2 = c + 2u - c_lo;
-                const unsigned s2 = k2 % kPipeStages, ph2 = (k2 / kPipeStages) & 1u;
-                unsigned landed;
-                asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                             : "=r"(landed) : "r"(smem_u32(&full[s2])), "r"(ph2) : "memory");
-                if (landed) {
-                    unsigned cell = 0;
-#pragma unroll
-                    for (int d = 0; d < N; ++d) {
-                        const T x = stage0[((size_t)s2 * N + d) * kPipeChunk + lane * (kPipeChunk / 32)];
-                        int k = to_int_sat((x - P.g0[d]) * P.inv_h[d]);
-                        k = max(0, min(k, P.L[d] - 2));
-                        cell += (unsigned)k * (unsigned)P.cstride[d];
-                    }
-                    const unsigned prev = __shfl_up_sync(0xffffffffu, cell, 1);
-                    if (lane == 0 || cell != prev) {
-                        const T* line = P.cells + (size_t)cell * (1 << N);
-                        if (PF == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
-                        else asm volatile("prefetch.global.L1 [%0];" ::"l"(line));
-                    }
-                }
-            }
             // from here on: interp_kernel's process()
             T p[N];
             bool oob = false;
