@@ -144,8 +144,11 @@ __device__ __forceinline__ void ld_record(const unsigned char* src, float& t0, f
 // ---------------------------------------------------------------------------------------------
 // Bin: the point loop of interp_kernel with the gather replaced by an append to the point's list.
 // ---------------------------------------------------------------------------------------------
+#ifndef NINT_BIN_ANA_CTAS
+#define NINT_BIN_ANA_CTAS 4  // resident CTAs the analytic variant is compiled for (5 and 6 measured: see DESIGN.md)
+#endif
 template <class T, bool IS_ND, int PRE, bool UNI, bool ANA = false>
-__global__ void __launch_bounds__(kBlock, 4) tile_bin_kernel(const __grid_constant__ Params<T> P,
+__global__ void __launch_bounds__(kBlock, ANA ? NINT_BIN_ANA_CTAS : 4) tile_bin_kernel(const __grid_constant__ Params<T> P,
                                                               const __grid_constant__ TileGeom G) {
     constexpr int N = 3;
     extern __shared__ __align__(16) unsigned char smem_pack[];
