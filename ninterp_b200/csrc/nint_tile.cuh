@@ -145,7 +145,8 @@ __device__ __forceinline__ void ld_record(const unsigned char* src, float& t0, f
 // Bin: the point loop of interp_kernel with the gather replaced by an append to the point's list.
 // ---------------------------------------------------------------------------------------------
 #ifndef NINT_BIN_ANA_CTAS
-#define NINT_BIN_ANA_CTAS 4  // resident CTAs the analytic variant is compiled for (5 and 6 measured: see DESIGN.md)
+#define NINT_BIN_ANA_CTAS 4  // resident CTAs the analytic variant is compiled for; 5 (48 registers) and 6 (40) spill and
+                            // measured slower: 16.3 -> 19.1 and 19.5 ms per 1e9 points
 #endif
 template <class T, bool IS_ND, int PRE, bool UNI, bool ANA = false>
 __global__ void __launch_bounds__(kBlock, ANA ? NINT_BIN_ANA_CTAS : 4) tile_bin_kernel(const __grid_constant__ Params<T> P,
