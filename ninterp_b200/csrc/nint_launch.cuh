@@ -43,11 +43,9 @@ template <class T, int N, bool IS_ND, int STRAT, int PRE, bool UNI>
 cudaError_t launch_pipe_variant(const Params<T>& P, const LaunchCfg& cfg) {
     auto kern = interp_pipe_kernel<T, N, IS_ND, STRAT, PRE, UNI>;
     const unsigned smem = (unsigned)(kPipeStages * N * kPipeChunk * sizeof(T)) + cfg.smem_bytes;
-    static thread_local unsigned configured = 0;
-    if (configured < smem) {
+    {  // per device and function: set on every launch (a host thread may drive several GPUs)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     static thread_local unsigned cached_smem = ~0u;
     static thread_local int cached_bps = 0;

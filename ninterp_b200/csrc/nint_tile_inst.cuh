@@ -60,11 +60,9 @@ cudaError_t launch_tile_eval<NINT_T>(const CUtensorMap& tmap, const TileEval<NIN
                                      const TileLaunch& cfg) {
     auto kern = tile_eval_kernel<NINT_T>;
     const unsigned smem = 2u * G.buf_bytes + (unsigned)(kEvalStages * kEvalChunk * kTileRecBytes);
-    static thread_local unsigned configured = 0;
-    if (configured < smem) {
+    {  // per device and function: set on every launch (a host thread may drive several GPUs)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     kern<<<(unsigned)cfg.sm_count, kEvalThreads, smem, (cudaStream_t)cfg.stream>>>(tmap, E, G);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
