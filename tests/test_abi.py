@@ -184,3 +184,20 @@ def test_argument_errors():
     assert _create_code(1, [[0., 1.]], np.zeros(2), 3, 4)[0] == -11
     # a hard-coded interpolator needs as many axes as value dimensions
     assert _create_code(0, [[0., 1.]], np.zeros((2, 2)), 0, 4)[0] == -10
+
+
+def test_host_result_buffer_checks():
+    # caller-supplied result buffers reach the C ABI as raw pointers: the mirror rejects a wrong dtype, a short,
+    # a read-only or a non-contiguous buffer before the call (no GPU needed for the check itself)
+    import ninterp_b200 as nb
+    from ninterp_b200.interpolator import _check_host_out
+
+    _check_host_out(np.empty(10), np.float64, 10)
+    _check_host_out(np.empty(12, dtype=np.float32), np.float32, 10)
+    for bad in (np.empty(10, dtype=np.float32), np.empty(9), np.empty(20)[::2], [0.0] * 10):
+        with pytest.raises(nb.EngineError):
+            _check_host_out(bad, np.float64, 10)
+    ro = np.empty(10)
+    ro.flags.writeable = False
+    with pytest.raises(nb.EngineError):
+        _check_host_out(ro, np.float64, 10)

@@ -526,3 +526,61 @@ def test_concurrent_batches_on_one_handle(monkeypatch):
             assert results[t] is not None, f"thread {t} failed"
             for got, st in results[t]:
                 assert_same(got, st, want, st_want, f"concurrent passes={passes} thread {t}")
+
+
+def test_f32_axis_spanning_more_than_flt_max():
+    # an f32 grid from -3e38 to 3e38: the span is finite in double but p - g[0] overflows in f32, so bucket and cell
+    # formulas cannot be used; such an axis takes the general path (full binary search, IEEE division)
+    from gpu_util import assert_same, expected_info, gpu_eval, make_pair
+
+    g = np.array([-3e38, -1e38, 1e38, 2e38, 3e38], dtype=np.float32)
+    v = np.array([1.0, -2.0, 4.0, 0.5, 3.0], dtype=np.float32)
+    q = np.array([0.5e38, -2.9e38, 2.5e38, 1e38, -1e38, 3e38, -3e38, 0.0, 3.3e38, np.nan, -np.inf] + list(np.linspace(-3e38, 3e38, 4001)),
+                 dtype=np.float32)
+    for kind in (FIXED, ND):
+        for strat in (LIN, NEA, LEFT, RIGHT) if kind == FIXED else (LIN, NEA):
+            for extrap in (ERROR, CLAMP, FILL) + ((ENABLE,) if strat == LIN else ()):
+                gi, o = make_pair(kind, [g], v, strat, extrap, fill=9.0, dtype=np.float32)
+                got, st, info = gpu_eval(gi, [q])
+                want, st_want = o.eval([q])
+                assert_same(got, st, want, st_want, f"wide f32 axis kind={kind} strat={strat} extrap={extrap}")
+                assert info == expected_info(st_want)
+    # and as one axis of a 2-D interpolator next to an ordinary one
+    g2 = np.linspace(0, 1, 7).astype(np.float32)
+    v2 = np.random.default_rng(1).uniform(-1, 1, (5, 7)).astype(np.float32)
+    cols = [q[:2000], np.random.default_rng(2).uniform(-0.1, 1.1, 2000).astype(np.float32)]
+    for strat in (LIN, NEA):
+        gi, o = make_pair(FIXED, [g, g2], v2, strat, CLAMP, dtype=np.float32)
+        got, st, _ = gpu_eval(gi, cols)
+        assert_same(got, st, *o.eval(cols), f"wide f32 axis in 2-D strat={strat}")
+
+
+def test_result_buffers_are_checked_and_setters_keep_the_mirror_consistent():
+    import torch
+
+    import ninterp_b200 as nb
+
+    g = nb.Interp2D([0., 1., 2.], [0., 1.], np.arange(6.).reshape(3, 2), nb.strategy.Linear, nb.Extrapolate.Error)
+    dev = torch.device("cuda", g.device)
+    cols = [torch.rand(100, dtype=torch.float64, device=dev) for _ in range(2)]
+    for bad in (dict(out=torch.empty(100, dtype=torch.float32, device=dev)), dict(out=torch.empty(50, dtype=torch.float64, device=dev)),
+                dict(out=torch.empty(100, dtype=torch.float64)), dict(status=torch.empty(100, dtype=torch.int32, device=dev)),
+                dict(status=torch.empty(10, dtype=torch.uint8, device=dev)), dict(info=torch.zeros(4, dtype=torch.int64)),
+                dict(out=torch.empty(200, dtype=torch.float64, device=dev)[::2])):
+        with pytest.raises(nb.EngineError):
+            g.interpolate_batch(cols, **bad)
+    with pytest.raises(nb.EngineError):
+        g.interpolate_batch_host(np.zeros((4, 2)), out=np.zeros(4, dtype=np.float32))
+    # a strategy the interpolator cannot take leaves the mirror and the handle unchanged (LeftNearest is 1-D only)
+    with pytest.raises(nb.EngineError):
+        g.set_strategy(nb.strategy.LeftNearest)
+    assert g.strategy == nb.strategy.Linear and g.interpolate([0.5, 0.5]) == 1.5
+    # the reference assigns the strategy before checking it (two/mod.rs set_strategy): Nearest + Enable fails and stays
+    g.set_extrapolate(nb.Extrapolate.Enable)
+    with pytest.raises(nb.ValidateError):
+        g.set_strategy(nb.strategy.Nearest)
+    assert g.strategy == nb.strategy.Nearest
+    # 0-D InterpND: set_extrapolate runs check_extrapolate too (n/mod.rs:342-346)
+    z = nb.InterpND([[]], [3.25], nb.strategy.Nearest, nb.Extrapolate.Error)
+    with pytest.raises(nb.ValidateError):
+        z.set_extrapolate(nb.Extrapolate.Enable)
