@@ -1131,6 +1131,9 @@ constexpr unsigned kSlabSpan = 32u * kSlabPer;  // points a warp scans at a time
 // point evaluation: at 64 registers (4 CTAs) it spills 60-170 bytes per thread and runs at 28.1 Gpoints/s on the
 // headline workload; at 80 registers (3 CTAs, no spills) 32.7; at 96 (2 CTAs) 31.4; at 48 (5 CTAs) 25.6.
 constexpr int slab_ctas(int n, int elem_bytes) { return n <= 3 ? 3 : min_ctas(n, elem_bytes); }
+#ifndef NINT_SLAB_AHEAD
+#define NINT_SLAB_AHEAD 1
+#endif
 #ifndef NINT_SLAB_ANA_CTAS
 #define NINT_SLAB_ANA_CTAS 3  // analytic variant (no node records): tried 4
 #endif
@@ -1189,9 +1192,24 @@ __global__ void __launch_bounds__(kBlock, (ANA && N == 3) ? NINT_SLAB_ANA_CTAS :
         if (P.status) P.status[i] = (uint8_t)status;
     };
 
-    for (unsigned span = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); span < nspans; span += warps) {
+    // axis-0 coordinates of a span, all requested before the first is used
+    auto scan_span = [&](unsigned span, T (&xs)[kSlabPer]) {
+#pragma unroll
+        for (int r = 0; r < kSlabPer; ++r) {
+            const unsigned j = span * kSlabSpan + r * 32u + lane;
+            xs[r] = (span < nspans && j < n) ? ld_stream(P.coords[0] + (size_t)j * P.coord_stride) : quiet_nan<T>();
+        }
+    };
+    const unsigned span0 = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    T xs[kSlabPer];
+    if (!INR) scan_span(span0, xs);
+    for (unsigned span = span0; span < nspans; span += warps) {
         const unsigned base = span * kSlabSpan;
         unsigned count = 0;
+        // the next span's scan is requested now, so that its DRAM round trip overlaps this span's evaluation
+        // (NINT_SLAB_AHEAD=0 builds request it at the top of its own turn, as round 1 did)
+        T xn[kSlabPer];
+        if (!INR && NINT_SLAB_AHEAD) scan_span(span + warps, xn);
         if (INR) {
             // members: inside the grid on every axis (NaN is outside: three/mod.rs:198-201).  The scan loads whole
             // points, normal priority: the members read theirs again a moment later.
@@ -1224,13 +1242,6 @@ __global__ void __launch_bounds__(kBlock, (ANA && N == 3) ? NINT_SLAB_ANA_CTAS :
                 count += __popc(bal);
             }
         } else {
-            // axis-0 coordinates of the span, all requested before the first is used
-            T xs[kSlabPer];
-#pragma unroll
-            for (int r = 0; r < kSlabPer; ++r) {
-                const unsigned j = base + r * 32u + lane;
-                xs[r] = (j < n) ? ld_stream(P.coords[0] + (size_t)j * P.coord_stride) : quiet_nan<T>();
-            }
             // members: axis-0 coordinate in (win_lo_x, win_hi_x]; the first window also takes everything below and
             // NaN, the last everything above.  Listed as offsets into the span, in any order.
 #pragma unroll
@@ -1271,6 +1282,14 @@ __global__ void __launch_bounds__(kBlock, (ANA && N == 3) ? NINT_SLAB_ANA_CTAS :
         if (lane >= ncarry && lane < ncarry + rem) carry = base + list[pos + lane - ncarry];
         ncarry += rem;
         __syncwarp();
+        if (!INR) {
+            if (NINT_SLAB_AHEAD) {
+#pragma unroll
+                for (int r = 0; r < kSlabPer; ++r) xs[r] = xn[r];
+            } else {
+                scan_span(span + warps, xs);
+            }
+        }
     }
     if (lane < ncarry) {
         Point<T, N> q;
