@@ -1131,8 +1131,10 @@ constexpr unsigned kSlabSpan = 32u * kSlabPer;  // points a warp scans at a time
 // point evaluation: at 64 registers (4 CTAs) it spills 60-170 bytes per thread and runs at 28.1 Gpoints/s on the
 // headline workload; at 80 registers (3 CTAs, no spills) 32.7; at 96 (2 CTAs) 31.4; at 48 (5 CTAs) 25.6.
 constexpr int slab_ctas(int n, int elem_bytes) { return n <= 3 ? 3 : min_ctas(n, elem_bytes); }
+// Requesting the next span's scan one span ahead overlaps its DRAM round trip with the evaluation: +2 % in f32 (50.9 ->
+// 52.0 Gpoints/s); in f64 the eight extra registers spill at 80 registers / 3 CTAs and it is slower (31 -> 35 ms).
 #ifndef NINT_SLAB_AHEAD
-#define NINT_SLAB_AHEAD 1
+#define NINT_SLAB_AHEAD (sizeof(T) == 4)
 #endif
 #ifndef NINT_SLAB_ANA_CTAS
 #define NINT_SLAB_ANA_CTAS 3  // analytic variant (no node records): tried 4
@@ -1206,8 +1208,7 @@ __global__ void __launch_bounds__(kBlock, (ANA && N == 3) ? NINT_SLAB_ANA_CTAS :
     for (unsigned span = span0; span < nspans; span += warps) {
         const unsigned base = span * kSlabSpan;
         unsigned count = 0;
-        // the next span's scan is requested now, so that its DRAM round trip overlaps this span's evaluation
-        // (NINT_SLAB_AHEAD=0 builds request it at the top of its own turn, as round 1 did)
+        // f32: the next span's scan is requested now, so that its DRAM round trip overlaps this span's evaluation
         T xn[kSlabPer];
         if (!INR && NINT_SLAB_AHEAD) scan_span(span + warps, xn);
         if (INR) {
