@@ -145,6 +145,7 @@ struct nint_handle {
     // binned route (nint_tile.cuh): tile geometry, TMA descriptor of the plain table, pool for the per-call lists
     bool tile_ready = false;
     nint::TileGeom tile_geom{};
+    double tile_halo = 1.0;  // staged elements per cell of a tile
     CUtensorMap tile_map{};
     cudaMemPool_t pool = nullptr;
     void* d_pt = nullptr;   // one point
@@ -658,7 +659,7 @@ bool tile_route(const nint_handle* h, size_t n, int windows) {
     // single pass 50.6 ms.  So the slab passes keep the batches they can take, and the binned tiles take the ones
     // they cannot: Extrapolate::Wrap, which re-maps coordinates across axes.
     if (windows > 0 && !forced) return false;
-    for (int d = 0; d < 3; ++d)
+    for (int d = 0; d < h->ndim_eff; ++d)
         if (!(h->ax[d].flags & nint::kAxisFast)) return false;
     const char* e_bytes = std::getenv("NINT_SLAB_MIN_BYTES");
     const char* e_points = std::getenv("NINT_SLAB_MIN_POINTS");
@@ -666,12 +667,12 @@ bool tile_route(const nint_handle* h, size_t n, int windows) {
     const long long min_points = e_points ? std::atoll(e_points) : 1ll << 22;
     if ((long long)n < min_points) return false;
     const double plain = (double)h->values_len * (double)elem_size(h->dtype);
-    const double single = h->d_cells ? plain * 8.0 : plain;
+    const double single = h->d_cells ? plain * (double)(1u << h->ndim_eff) : plain;
     if (single < (double)min_bytes) return false;
-    // every superchunk streams the table once: beyond ~40 bytes per point of that the slab passes or the single
-    // pass are the better deal
-    const double per_point = plain * 1.2 / (double)(1ull << h->tile_geom.sc_shift);
-    if (!forced && per_point > 48.0) return false;
+    // every superchunk streams the table (with the tiles' halo) once: beyond ~70 bytes per point of that the single
+    // pass is the better deal
+    const double per_point = plain * h->tile_halo / (double)(1ull << h->tile_geom.sc_shift);
+    if (!forced && per_point > 72.0) return false;
     return true;
 }
 
@@ -679,41 +680,69 @@ bool tile_route(const nint_handle* h, size_t n, int windows) {
 // not 16-byte multiples, no driver entry point): the route is simply not offered.
 void build_tile(nint_handle* h) {
     h->tile_ready = false;
-    if (h->constant || h->ndim_eff != 3 || h->strategy != NINT_LINEAR) return;
+    const int N = h->ndim_eff;
+    if (h->constant || N < 3 || N > nint::kTileMaxDim || h->strategy != NINT_LINEAR) return;
+    if (h->kind == NINT_KIND_FIXED && N != 3) return;
     const size_t es = elem_size(h->dtype);
-    const size_t L0 = h->axis_len[0], L1 = h->axis_len[1], L2 = h->axis_len[2];
-    if (L0 < 2 || L1 < 2 || L2 < 2) return;
-    if ((L2 * es) % 16 != 0) return;  // cuTensorMapEncodeTiled: global strides are multiples of 16 bytes
+    for (int d = 0; d < N; ++d)
+        if (h->axis_len[d] < 2) return;
+    if ((h->axis_len[N - 1] * es) % 16 != 0) return;  // cuTensorMapEncodeTiled: global strides are multiples of 16 bytes
     nint::TileGeom& g = h->tile_geom;
     g = nint::TileGeom{};
-    // cells per tile: 16 x 16 x 32 doubles (17 x 17 x 34 staged, 78.6 KB) or 16 x 32 x 32 floats (80.8 KB): two
-    // buffers fill one SM's shared memory
-    g.sh[0] = 4;
-    g.sh[1] = (es == 8) ? 4 : 5;
-    g.sh[2] = 5;
-    if (const char* env = std::getenv("NINT_TILE_SH")) {  // tuning: "a,b,c" = log2(cells per tile) per axis, at most the default
-        int a = 0, b = 0, c = 0;
-        if (std::sscanf(env, "%d,%d,%d", &a, &b, &c) == 3) {
-            g.sh[0] = std::max(1, std::min(a, g.sh[0]));
-            g.sh[1] = std::max(1, std::min(b, g.sh[1]));
-            g.sh[2] = std::max(1, std::min(c, g.sh[2]));
+    g.ndim = N;
+    const int inner_q = (int)(16 / es);
+    auto box_bytes = [&](const int* sh) {
+        unsigned long long vol = 1;
+        for (int d = 0; d < N; ++d) {
+            int b = (1 << sh[d]) + 1;
+            if (d == N - 1) b = (b + inner_q - 1) / inner_q * inner_q;
+            vol *= (unsigned long long)b;
+        }
+        return vol * es;
+    };
+    if (N == 3) {
+        // cells per tile: 16 x 16 x 32 doubles (17 x 17 x 34 staged, 78.6 KB) or 16 x 32 x 32 floats (80.8 KB): two
+        // buffers and the record stages fill one SM's shared memory
+        g.sh[0] = 4;
+        g.sh[1] = (es == 8) ? 4 : 5;
+        g.sh[2] = 5;
+    } else {
+        // four and five axes: grow the tile from 2 cells per axis, innermost axis first, while two buffers still fit
+        // beside the record stages (the halo of such tiles is 3-4x: DESIGN.md section 5)
+        const unsigned long long budget = 80ull * 1024;
+        for (int d = 0; d < N; ++d) g.sh[d] = 1;
+        for (bool grew = true; grew;) {
+            grew = false;
+            for (int d = N - 1; d >= 0; --d) {
+                if (g.sh[d] >= nint::kLocBits - 1 || (1u << g.sh[d]) >= h->axis_len[d] - 1) continue;
+                ++g.sh[d];
+                if (box_bytes(g.sh) <= budget) grew = true;
+                else --g.sh[d];
+            }
         }
     }
+    if (const char* env = std::getenv("NINT_TILE_SH")) {  // tuning: "a,b,c[,d,e]" = log2(cells per tile) per axis, at most the default
+        int v[5] = {0, 0, 0, 0, 0};
+        if (std::sscanf(env, "%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4]) >= N)
+            for (int d = 0; d < N; ++d) g.sh[d] = std::max(1, std::min(v[d], g.sh[d]));
+    }
     unsigned long long ntiles = 1, vol = 1;
-    for (int d = 0; d < 3; ++d) {
+    for (int d = 0; d < N; ++d) {
         const int cells = (int)h->axis_len[d] - 1;
         g.nt[d] = (cells + (1 << g.sh[d]) - 1) >> g.sh[d];
         g.box[d] = (1 << g.sh[d]) + 1;
         ntiles *= (unsigned long long)g.nt[d];
     }
-    const int inner_q = (int)(16 / es);
-    g.box[2] = (g.box[2] + inner_q - 1) / inner_q * inner_q;
-    for (int d = 0; d < 3; ++d) vol *= (unsigned long long)g.box[d];
+    g.box[N - 1] = (g.box[N - 1] + inner_q - 1) / inner_q * inner_q;
+    for (int d = 0; d < N; ++d) vol *= (unsigned long long)g.box[d];
     if (ntiles > (1ull << 20)) return;
     g.ntiles = (int)ntiles;
     g.tile_bytes = (unsigned)(vol * es);
     g.buf_bytes = (g.tile_bytes + 127u) & ~127u;
-    unsigned sc_shift = 22;  // 4 Mi points: a 32 MB window of f64 results stays in L2; 2^23 measured 30 % slower
+    g.rec_bytes = (unsigned)(((size_t)N * es + 8 <= 32) ? 32 : (((size_t)N * es + 8 <= 48) ? 48 : 64));
+    // a superchunk's window of `out` has to stay in L2 while its tiles are walked: 32 MB, i.e. 2^22 f64 / 2^23 f32 points
+    // (a 64 MB window measured 30 % slower: every 8-byte result store then misses)
+    unsigned sc_shift = (es == 8) ? 22 : 23;
     if (const char* env = std::getenv("NINT_TILE_SC_SHIFT")) sc_shift = (unsigned)std::atoi(env);
     g.sc_shift = std::min(28u, std::max(10u, sc_shift));
     const unsigned long long per_list = (1ull << g.sc_shift) / ntiles;
@@ -724,6 +753,7 @@ void build_tile(nint_handle* h) {
     const unsigned long long page = 1ull << g.page_shift;
     g.rounds = (unsigned)((per_list + per_list / 4 + 256 + page - 1) / page);
     g.cap = g.rounds << g.page_shift;
+    h->tile_halo = (double)vol / (double)(1ull << (g.sh[0] + g.sh[1] + g.sh[2] + (N > 3 ? g.sh[3] : 0) + (N > 4 ? g.sh[4] : 0)));
 
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -735,13 +765,19 @@ void build_tile(nint_handle* h) {
         cudaGetLastError();
         return;
     }
-    const cuuint64_t gdim[3] = {L2, L1, L0};
-    const cuuint64_t gstride[2] = {L2 * es, L1 * L2 * es};
-    const cuuint32_t box[3] = {(cuuint32_t)g.box[2], (cuuint32_t)g.box[1], (cuuint32_t)g.box[0]};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = ((EncodeFn)fn)(&h->tile_map, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t box[5], estr[5];
+    unsigned long long run = es;
+    for (int j = 0; j < N; ++j) {  // TMA dimension j is axis N-1-j: innermost first
+        gdim[j] = h->axis_len[N - 1 - j];
+        box[j] = (cuuint32_t)g.box[N - 1 - j];
+        estr[j] = 1;
+        run *= h->axis_len[N - 1 - j];
+        if (j < N - 1) gstride[j] = run;
+    }
+    const CUresult r = ((EncodeFn)fn)(&h->tile_map, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)N,
                                       h->d_values, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,  // box rows are 272 B: promoted to 256 B they fetch 512
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,  // box rows are short (272 B in 3-D f64): promoted to 256 B they fetch 512
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return;
     if (!h->pool) {
@@ -791,7 +827,7 @@ int launch_tiles(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
     const unsigned long long n = P.n;
     const unsigned max_sc = (unsigned)((std::min(n, seg) + (1ull << G.sc_shift) - 1) >> G.sc_shift);
     const size_t cursor_bytes = (size_t)max_sc * (size_t)G.ntiles * nint::kCursorStride * sizeof(unsigned);
-    const size_t record_bytes = (size_t)max_sc * (size_t)G.ntiles * (size_t)G.cap * nint::kTileRecBytes;
+    const size_t record_bytes = (size_t)max_sc * (size_t)G.ntiles * (size_t)G.cap * (size_t)G.rec_bytes;
     unsigned char* scratch = nullptr;
     if (cudaMallocFromPoolAsync((void**)&scratch, cursor_bytes + record_bytes + 256, h->pool, stream) != cudaSuccess) {
         cudaGetLastError();
@@ -801,6 +837,7 @@ int launch_tiles(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
     G.records = scratch + ((cursor_bytes + 255) & ~(size_t)255);
     G.records_bytes = record_bytes;
     nint::TileLaunch tl;
+    tl.ndim = cfg.ndim;
     tl.is_nd = cfg.is_nd;
     tl.all_uniform = cfg.all_uniform;
     tl.all_analytic = 1;
@@ -811,14 +848,15 @@ int launch_tiles(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
     tl.smem_bytes = cfg.smem_bytes;
     tl.stream = stream;
     const size_t es = sizeof(T);
-    const T* cols0[3] = {P.coords[0], P.coords[1], P.coords[2]};
+    const T* cols0[nint::kTileMaxDim];
+    for (int d = 0; d < cfg.ndim; ++d) cols0[d] = P.coords[d];
     T* out0 = P.out;
     uint8_t* st0 = P.status;
     const unsigned long long base0 = P.index_base;
     int rc = NINT_OK;
     for (unsigned long long start = 0; start < n && rc == NINT_OK; start += seg) {
         const unsigned long long m = std::min(seg, n - start);
-        for (int d = 0; d < 3; ++d) P.coords[d] = cols0[d] + start * P.coord_stride;
+        for (int d = 0; d < cfg.ndim; ++d) P.coords[d] = cols0[d] + start * P.coord_stride;
         P.out = out0 + start;
         P.status = st0 ? st0 + start : nullptr;
         P.n = m;

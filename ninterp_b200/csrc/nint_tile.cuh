@@ -1,20 +1,20 @@
-// nint_tile.cuh — the binned route for incoherent queries on 3-D tables beyond L2 (Linear).
+// nint_tile.cuh — the binned route for incoherent queries on 3-D to 5-D tables beyond L2 (Linear).
 //
-// A random cell of a table that does not fit L2 costs 4-5 DRAM sectors, and even with an L2-resident slab the
-// gathers are bound by L2 sector bandwidth.  This route takes the gathers out of the memory
+// A random cell of a table that does not fit L2 costs 2^(N-1) DRAM sectors or more, and even with an L2-resident slab
+// the gathers are bound by L2 sector bandwidth.  This route takes the gathers out of the memory
 // system altogether: queries are bucketed by grid tile and every tile's value sub-block is staged once in shared
 // memory by TMA (cp.async.bulk.tensor, UTMALDG), where the 2^N corner loads are LDS.
 //
 //   tile_bin_kernel   one point per thread: front-end, cell guess + verification and the weights t_d exactly as the
 //                     single pass computes them (fast_weights == first half of fast_point); the point's record
-//                     {t_0, t_1, t_2, index, cell inside the tile} is appended to the list of its (superchunk, tile)
+//                     {t_0 .. t_{N-1}, index, cell inside the tile} is appended to the list of its (superchunk, tile)
 //                     with one global atomic.  Points that need the general path are finished here.
 //   tile_eval_kernel  persistent CTAs walk the (superchunk, tile) lists superchunk-major: TMA brings the tile's
-//                     (B0+1) x (B1+1) x (B2+1) values into shared memory (double buffered, mbarrier), the records are
-//                     read coalesced, blended from shared memory with the reference's operation order
-//                     (three/strategies.rs:37-49) and the results scattered to out[index].  A superchunk is 2^23
-//                     consecutive points, so the scatter stays inside a 64 MB window of `out` that L2 merges into
-//                     full lines before it reaches DRAM.
+//                     prod(B_d + 1) values into shared memory (ring of two, mbarrier), the records arrive by
+//                     cp.async.bulk, are blended from shared memory with the reference's operation order
+//                     (three/strategies.rs:37-49, n/strategies.rs:86-104) and the results scattered to out[index].
+//                     A superchunk is 2^22 (f64) / 2^23 (f32) consecutive points, so the scatter stays inside a 32 MB
+//                     window of `out` that L2 merges into full lines before it reaches DRAM.
 //
 // The arithmetic is the single pass's: t_d is computed once (bin) by the same inlined functions and the blend uses
 // the same expression tree, so results are bit-identical whichever route a batch takes.
@@ -26,35 +26,45 @@
 
 namespace nint {
 
-constexpr unsigned kCursorStride = 8;   // u32 slots between list cursors: 32 bytes, so neighbours hit different L2 slices
-constexpr int kTileRecBytes = 32;
+constexpr unsigned kCursorStride = 8;  // u32 slots between list cursors: 32 bytes, so neighbours hit different L2 slices
+constexpr int kTileMaxDim = 5;         // TMA tensor maps have at most five dimensions
+constexpr int kLocBits = 6;            // bits per axis of a record's cell-inside-the-tile field (tiles of at most 64 cells per axis)
+
+// A record: N weights in T, padding, then {point index, cell inside the tile} in the last 8 bytes.
+template <class T, int N>
+__host__ __device__ constexpr int tile_rec_bytes() {
+    return (N * (int)sizeof(T) + 8 <= 32) ? 32 : ((N * (int)sizeof(T) + 8 <= 48) ? 48 : 64);
+}
 
 // Geometry of the binned route, shared by both kernels.
 struct TileGeom {
-    int sh[3];            // log2(cells per tile) along each axis
-    int nt[3];            // tiles per axis
+    int ndim;
+    int sh[kTileMaxDim];   // log2(cells per tile) along each axis
+    int nt[kTileMaxDim];   // tiles per axis
     int ntiles;
-    int box[3];           // staged elements per axis: cells per tile + 1 (innermost padded to a 16-byte multiple)
-    unsigned tile_bytes;  // bytes TMA delivers per tile (box volume x sizeof(T))
-    unsigned buf_bytes;   // tile_bytes rounded up to 128
-    unsigned cap;         // records per (superchunk, tile) list: rounds << page_shift
-    unsigned page_shift;  // log2(records per page).  A list is stored as pages interleaved over the tiles of its
-    unsigned rounds;      // superchunk: page r of every tile, then page r + 1, ...  Lists grow at the same pace when the
-                          // queries are spread evenly, so the appends of a moment land in a few MB instead of one spot
-                          // per list over hundreds of MB (one TLB miss per 32-byte record otherwise)
-    unsigned sc_shift;    // log2(points per superchunk)
-    unsigned n_sc;        // superchunks in this launch
-    unsigned flags;       // tuning (NINT_TILE_FLAGS): 1 = record stores evict-first, 2 = no evict-first hint on the record
-                          // and tile loads, 4 = no evict-last hint on the result stores, 8 = no result stores at all (measurement only), 16 = no prefetch of the result window
+    int box[kTileMaxDim];  // staged elements per axis: cells per tile + 1 (innermost padded to a 16-byte multiple)
+    unsigned tile_bytes;   // bytes TMA delivers per tile (box volume x sizeof(T))
+    unsigned buf_bytes;    // tile_bytes rounded up to 128
+    unsigned rec_bytes;    // tile_rec_bytes<T, N>()
+    unsigned cap;          // records per (superchunk, tile) list: rounds << page_shift
+    unsigned page_shift;   // log2(records per page).  A list is stored as pages interleaved over the tiles of its
+    unsigned rounds;       // superchunk: page r of every tile, then page r + 1, ...  Lists grow at the same pace when the
+                           // queries are spread evenly, so the appends of a moment land in a few MB instead of one spot
+                           // per list over hundreds of MB (one TLB miss per record otherwise)
+    unsigned sc_shift;     // log2(points per superchunk)
+    unsigned n_sc;         // superchunks in this launch
+    unsigned flags;        // tuning (NINT_TILE_FLAGS): 2 = no evict-first hint on the record and tile loads, 4 = no
+                           // evict-last hint on the result stores, 8 = no result stores at all (measurement only),
+                           // 16 = no prefetch of the result window
     unsigned long long records_bytes;  // size of `records` (bounds-checked builds)
-    unsigned* cursor;     // [n_sc * ntiles] list lengths, kCursorStride apart
-    unsigned char* records;  // [n_sc * ntiles][cap] records of kTileRecBytes
+    unsigned* cursor;      // [n_sc * ntiles] list lengths, kCursorStride apart
+    unsigned char* records;  // [n_sc][rounds][ntiles][1 << page_shift] records
 };
 
 // Byte offset of record `slot` of list (sc, tile).
 __device__ __forceinline__ size_t record_offset(const TileGeom& G, unsigned sc, unsigned tile, unsigned slot) {
     const size_t page = ((size_t)sc * G.rounds + (slot >> G.page_shift)) * (size_t)G.ntiles + tile;
-    return ((page << G.page_shift) + (slot & ((1u << G.page_shift) - 1u))) * (size_t)kTileRecBytes;
+    return ((page << G.page_shift) + (slot & ((1u << G.page_shift) - 1u))) * (size_t)G.rec_bytes;
 }
 
 // First half of fast_point() for Linear: cell guess, verification and weights of every axis.  Same functions, same
@@ -102,43 +112,48 @@ __device__ __forceinline__ T blend_cube(T (&cube)[1 << N], const T (&t)[N]) {
     return cube[0];
 }
 
-__device__ __forceinline__ void st_record_cs(unsigned char* dst, double t0, double t1, double t2, unsigned idx, unsigned loc) {
-    const unsigned long long meta = (unsigned long long)idx | ((unsigned long long)loc << 32);
-    asm volatile("st.global.cs.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "l"(__double_as_longlong(t0)),
-                 "l"(__double_as_longlong(t1)), "l"(__double_as_longlong(t2)), "l"(meta)
-                 : "memory");
+// Record I/O.  Stored with default L2 priority: the 2 KB page a list is filling stays in L2 until its lines are
+// complete (evict-first sectors leave one by one and turn into partial-line DRAM writes).
+template <class T, int N>
+__device__ __forceinline__ void st_record(unsigned char* dst, const T (&t)[N], unsigned idx, unsigned loc) {
+    constexpr int W = tile_rec_bytes<T, N>() / 8;
+    unsigned long long w[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) w[i] = 0ull;
+    if constexpr (sizeof(T) == 8) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) w[d] = (unsigned long long)__double_as_longlong((double)t[d]);
+    } else {
+#pragma unroll
+        for (int d = 0; d < N; ++d) w[d / 2] |= (unsigned long long)__float_as_uint((float)t[d]) << (32 * (d & 1));
+    }
+    w[W - 1] = (unsigned long long)idx | ((unsigned long long)loc << 32);
+#pragma unroll
+    for (int i = 0; i + 4 <= W; i += 4)
+        asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(dst + 8 * i), "l"(w[i]), "l"(w[i + 1]), "l"(w[i + 2]), "l"(w[i + 3]) : "memory");
+    if constexpr (W % 4 == 2)
+        asm volatile("st.global.v2.b64 [%0], {%1,%2};" ::"l"(dst + 8 * (W - 2)), "l"(w[W - 2]), "l"(w[W - 1]) : "memory");
 }
-__device__ __forceinline__ void st_record(unsigned char* dst, double t0, double t1, double t2, unsigned idx, unsigned loc) {
-    const unsigned long long meta = (unsigned long long)idx | ((unsigned long long)loc << 32);
-    // default L2 priority: the 2 KB page a list is filling stays in L2 until its lines are complete (evict-first
-    // sectors leave one by one and turn into partial-line DRAM writes)
-    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "l"(__double_as_longlong(t0)),
-                 "l"(__double_as_longlong(t1)), "l"(__double_as_longlong(t2)), "l"(meta)
-                 : "memory");
-}
-__device__ __forceinline__ void ld_record(const unsigned char* src, double& t0, double& t1, double& t2, unsigned& idx,
-                                          unsigned& loc) {
-    long long a, b, c;
-    unsigned long long meta;
-    asm volatile("ld.global.cs.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(meta) : "l"(src));
-    t0 = __longlong_as_double(a);
-    t1 = __longlong_as_double(b);
-    t2 = __longlong_as_double(c);
-    idx = (unsigned)meta;
-    loc = (unsigned)(meta >> 32);
-}
-
-// f32 interpolators use the same 32-byte record (the weights widen exactly)
-__device__ __forceinline__ void st_record(unsigned char* dst, float t0, float t1, float t2, unsigned idx, unsigned loc) {
-    st_record(dst, (double)t0, (double)t1, (double)t2, idx, loc);
-}
-__device__ __forceinline__ void ld_record(const unsigned char* src, float& t0, float& t1, float& t2, unsigned& idx,
-                                          unsigned& loc) {
-    double a, b, c;
-    ld_record(src, a, b, c, idx, loc);
-    t0 = (float)a;
-    t1 = (float)b;
-    t2 = (float)c;
+// from a record stage in shared memory
+template <class T, int N>
+__device__ __forceinline__ void ld_record_shared(const unsigned char* src, T (&t)[N], unsigned& idx, unsigned& loc) {
+    constexpr int W = tile_rec_bytes<T, N>() / 8;
+    unsigned long long w[W];
+#pragma unroll
+    for (int i = 0; i < W; i += 2) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(src + 8 * i);
+        w[i] = v.x;
+        w[i + 1] = v.y;
+    }
+    if constexpr (sizeof(T) == 8) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) t[d] = (T)__longlong_as_double((long long)w[d]);
+    } else {
+#pragma unroll
+        for (int d = 0; d < N; ++d) t[d] = (T)__uint_as_float((unsigned)(w[d / 2] >> (32 * (d & 1))));
+    }
+    idx = (unsigned)w[W - 1];
+    loc = (unsigned)(w[W - 1] >> 32);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -148,10 +163,11 @@ __device__ __forceinline__ void ld_record(const unsigned char* src, float& t0, f
 #define NINT_BIN_ANA_CTAS 4  // resident CTAs the analytic variant is compiled for; 5 (48 registers) and 6 (40) spill and
                             // measured slower: 16.3 -> 19.1 and 19.5 ms per 1e9 points
 #endif
-template <class T, bool IS_ND, int PRE, bool UNI, bool ANA = false>
-__global__ void __launch_bounds__(kBlock, ANA ? NINT_BIN_ANA_CTAS : 4) tile_bin_kernel(const __grid_constant__ Params<T> P,
-                                                              const __grid_constant__ TileGeom G) {
-    constexpr int N = 3;
+constexpr int bin_ctas(int n, bool ana) { return n == 3 ? (ana ? NINT_BIN_ANA_CTAS : 4) : 2; }
+
+template <class T, int N, bool IS_ND, int PRE, bool UNI, bool ANA = false>
+__global__ void __launch_bounds__(kBlock, bin_ctas(N, ANA)) tile_bin_kernel(const __grid_constant__ Params<T> P,
+                                                                            const __grid_constant__ TileGeom G) {
     extern __shared__ __align__(16) unsigned char smem_pack[];
     if (P.mode_flag != nullptr && *P.mode_flag != P.mode_want) return;
     {
@@ -193,17 +209,19 @@ __global__ void __launch_bounds__(kBlock, ANA ? NINT_BIN_ANA_CTAS : 4) tile_bin_
         const bool fast = ANA ? fast_weights_analytic<T, N, IS_ND, PRE == kPreClamp>(P, p, k, t)
                               : fast_weights<T, N, IS_ND, UNI, PRE == kPreClamp>(P, pack, p, k, t);
         if (fast) {
-            const unsigned tile = (unsigned)(((k[0] >> G.sh[0]) * G.nt[1] + (k[1] >> G.sh[1])) * G.nt[2] + (k[2] >> G.sh[2]));
-            const unsigned loc = (unsigned)(k[0] & ((1 << G.sh[0]) - 1)) | ((unsigned)(k[1] & ((1 << G.sh[1]) - 1)) << 8) |
-                                 ((unsigned)(k[2] & ((1 << G.sh[2]) - 1)) << 16);
+            unsigned tile = 0, loc = 0;
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                tile = tile * (unsigned)G.nt[d] + (unsigned)(k[d] >> G.sh[d]);
+                loc |= (unsigned)(k[d] & ((1 << G.sh[d]) - 1)) << (kLocBits * d);
+            }
             const unsigned sc = i >> G.sc_shift;
             const unsigned list = sc * (unsigned)G.ntiles + tile;
             NINT_ASSERT(sc < G.n_sc && tile < (unsigned)G.ntiles);
             const unsigned slot = atomicAdd(G.cursor + (size_t)list * kCursorStride, 1u);
             if (slot < G.cap) {
-                NINT_ASSERT(record_offset(G, sc, tile, slot) + kTileRecBytes <= G.records_bytes);
-                if (G.flags & 1u) st_record_cs(G.records + record_offset(G, sc, tile, slot), (double)t[0], (double)t[1], (double)t[2], i, loc);
-                else st_record(G.records + record_offset(G, sc, tile, slot), t[0], t[1], t[2], i, loc);
+                NINT_ASSERT(record_offset(G, sc, tile, slot) + G.rec_bytes <= G.records_bytes);
+                st_record<T, N>(G.records + record_offset(G, sc, tile, slot), t, i, loc);
             } else {
                 // list full (queries far from uniform): finish the point here from the plain table
                 long long base = 0;
@@ -262,14 +280,29 @@ __global__ void __launch_bounds__(kBlock, ANA ? NINT_BIN_ANA_CTAS : 4) tile_bin_
 // ---------------------------------------------------------------------------------------------
 // Evaluate: TMA-staged tiles, records blended from shared memory.
 // ---------------------------------------------------------------------------------------------
-// One tile: box (box[2], box[1], box[0]) of the table at element coordinates (c0 innermost) -> shared memory.
-__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1,
-                                              int c2, unsigned long long pol) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(pol)
-        : "memory");
+// One tile: the box of the table at element coordinates c (c[N-1] innermost) -> shared memory.
+template <int N>
+__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, unsigned long long* bar, const int (&c)[N],
+                                              unsigned long long pol) {
+    if constexpr (N == 3) {
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+                smem_u32(dst)),
+            "l"(map), "r"(c[2]), "r"(c[1]), "r"(c[0]), "r"(smem_u32(bar)), "l"(pol)
+            : "memory");
+    } else if constexpr (N == 4) {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;" ::"r"(
+                smem_u32(dst)),
+            "l"(map), "r"(c[3]), "r"(c[2]), "r"(c[1]), "r"(c[0]), "r"(smem_u32(bar)), "l"(pol)
+            : "memory");
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;" ::"r"(
+                smem_u32(dst)),
+            "l"(map), "r"(c[4]), "r"(c[3]), "r"(c[2]), "r"(c[1]), "r"(c[0]), "r"(smem_u32(bar)), "l"(pol)
+            : "memory");
+    }
 }
 
 template <class T>
@@ -282,22 +315,23 @@ struct TileEval {
 
 // One CTA per SM: warp 0 is the producer (one lane drives the TMA engine), kEvalConsumers threads evaluate.
 //   tile ring    2 buffers   producer: UTMALDG of the item's tile        consumers: corner loads (LDS)
-//   record ring  kEvalStages buffers of kEvalChunk records, UBLKCP page by page; one record per consumer thread
+//   record ring  stages of kEvalChunk records, UBLKCP page by page; one record per consumer thread
 // Every buffer has a `full` (transaction-count) and an `empty` (one arrival per consumer warp) mbarrier, so record
 // and tile traffic of the items ahead is in flight while the current records are blended: nothing waits on DRAM
 // latency.  Both roles walk the same item sequence (the lists are complete before this kernel starts).
 constexpr int kEvalConsumers = 512;
 constexpr int kEvalThreads = kEvalConsumers + 32;
-constexpr int kEvalStages = 4;
 constexpr int kEvalChunk = kEvalConsumers;  // records per stage
+__host__ __device__ constexpr int eval_stages(int rec_bytes) { return rec_bytes == 32 ? 4 : 2; }  // 64 KB (48 KB) of record stages
 
-template <class T>
+template <class T, int N>
 __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                      const __grid_constant__ TileEval<T> E,
                                                                      const __grid_constant__ TileGeom G) {
-    constexpr int N = 3;
+    constexpr int kRec = tile_rec_bytes<T, N>();
+    constexpr int kStages = eval_stages(kRec);
     extern __shared__ __align__(128) unsigned char smem_dyn[];
-    __shared__ __align__(8) unsigned long long tile_full[2], tile_empty[2], rec_full[kEvalStages], rec_empty[kEvalStages];
+    __shared__ __align__(8) unsigned long long tile_full[2], tile_empty[2], rec_full[kStages], rec_empty[kStages];
     if (E.mode_flag != nullptr && *E.mode_flag != E.mode_want) return;
     const unsigned tid = threadIdx.x;
     unsigned char* const tiles = smem_dyn;
@@ -307,7 +341,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
             mbar_init(&tile_full[b], 1);
             mbar_init(&tile_empty[b], kEvalConsumers / 32);
         }
-        for (int s = 0; s < kEvalStages; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             mbar_init(&rec_full[s], 1);
             mbar_init(&rec_empty[s], kEvalConsumers / 32);
         }
@@ -327,19 +361,22 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
         if (tid != 0) return;
         // ---------------------------------------------------------------- producer
         // records and tiles are used once per superchunk: evict-first, so that the window of `out` the superchunk
-        // scatters into (8 bytes x 2^sc_shift) stays in L2 until its sectors are complete
+        // scatters into stays in L2 until its sectors are complete
         const unsigned long long stream_pol = (G.flags & 2u) ? make_table_policy(0.0f) : l2_policy_evict_first();
         unsigned tb = 0, tb_phase = 0, st = 0, st_phase = 0;
         // the tile of the NEXT item is requested before the records of the current one: the record stages only free
         // up as the consumers work through the item, and a tile requested after them would land too late
         auto request_tile = [&](unsigned item) {
-            const int tile = (int)(item % (unsigned)G.ntiles);
-            const int t2 = tile % G.nt[2];
-            const int t1 = (tile / G.nt[2]) % G.nt[1];
-            const int t0 = tile / (G.nt[2] * G.nt[1]);
+            unsigned tile = item % (unsigned)G.ntiles;
+            int c[N];
+#pragma unroll
+            for (int d = N - 1; d >= 0; --d) {
+                c[d] = (int)(tile % (unsigned)G.nt[d]) << G.sh[d];
+                tile /= (unsigned)G.nt[d];
+            }
             mbar_wait(&tile_empty[tb], tb_phase ^ 1u);
             mbar_expect_tx(&tile_full[tb], G.tile_bytes);
-            tma_load_tile(tiles + (size_t)tb * G.buf_bytes, &tmap, &tile_full[tb], t2 << G.sh[2], t1 << G.sh[1], t0 << G.sh[0], stream_pol);
+            tma_load_tile<N>(tiles + (size_t)tb * G.buf_bytes, &tmap, &tile_full[tb], c, stream_pol);
             tb ^= 1u;
             tb_phase ^= (tb == 0u);
         };
@@ -354,18 +391,18 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
             for (unsigned base = 0; base < count; base += kEvalChunk) {
                 const unsigned m = min((unsigned)kEvalChunk, count - base);
                 mbar_wait(&rec_empty[st], st_phase ^ 1u);
-                mbar_expect_tx(&rec_full[st], m * kTileRecBytes);
-                unsigned char* dst = stages + (size_t)st * (kEvalChunk * kTileRecBytes);
+                mbar_expect_tx(&rec_full[st], m * kRec);
+                unsigned char* dst = stages + (size_t)st * (kEvalChunk * kRec);
                 // page by page: a piece never crosses a page boundary
                 for (unsigned slot = base; slot < base + m;) {
                     const unsigned in_page = slot & ((1u << G.page_shift) - 1u);
                     const unsigned len = min((1u << G.page_shift) - in_page, base + m - slot);
-                    NINT_ASSERT(record_offset(G, sc, tile, slot) + (size_t)len * kTileRecBytes <= G.records_bytes);
-                    bulk_load(dst + (size_t)(slot - base) * kTileRecBytes, G.records + record_offset(G, sc, tile, slot),
-                              len * kTileRecBytes, &rec_full[st], stream_pol);
+                    NINT_ASSERT(record_offset(G, sc, tile, slot) + (size_t)len * kRec <= G.records_bytes);
+                    bulk_load(dst + (size_t)(slot - base) * kRec, G.records + record_offset(G, sc, tile, slot), len * kRec,
+                              &rec_full[st], stream_pol);
                     slot += len;
                 }
-                if (++st == kEvalStages) {
+                if (++st == kStages) {
                     st = 0;
                     st_phase ^= 1u;
                 }
@@ -377,8 +414,10 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
     // -------------------------------------------------------------------- consumers
     const unsigned ct = tid - 32u;
     const unsigned lane = tid & 31u;
-    const int sy = G.box[2];
-    const int sx = G.box[1] * G.box[2];
+    int stride[N];  // element strides of the staged tile
+    stride[N - 1] = 1;
+#pragma unroll
+    for (int d = N - 2; d >= 0; --d) stride[d] = stride[d + 1] * G.box[d + 1];
     const unsigned long long keep_pol = (G.flags & 4u) ? make_table_policy(0.0f) : l2_policy_evict_last();
     unsigned tb = 0, tb_phase = 0, st = 0, st_phase = 0;
     unsigned window_sc = ~0u;
@@ -405,30 +444,33 @@ __global__ void __launch_bounds__(kEvalThreads, 1) tile_eval_kernel(const __grid
             const unsigned m = min((unsigned)kEvalChunk, count - base);
             mbar_wait(&rec_full[st], st_phase);
             if (ct < m) {
-                const unsigned char* rp = stages + (size_t)st * (kEvalChunk * kTileRecBytes) + (size_t)ct * kTileRecBytes;
-                const double2 r0 = *reinterpret_cast<const double2*>(rp);
-                const double2 r1 = *reinterpret_cast<const double2*>(rp + 16);
-                T t[N] = {(T)r0.x, (T)r0.y, (T)r1.x};
-                const unsigned long long meta = (unsigned long long)__double_as_longlong(r1.y);
-                const unsigned idx = (unsigned)meta, loc = (unsigned)(meta >> 32);
-                const int off = (int)(loc & 0xffu) * sx + (int)((loc >> 8) & 0xffu) * sy + (int)(loc >> 16);
-                NINT_ASSERT(idx < E.n && (unsigned)(off + sx + sy + 1) * sizeof(T) < G.tile_bytes);
+                T t[N];
+                unsigned idx, loc;
+                ld_record_shared<T, N>(stages + (size_t)st * (kEvalChunk * kRec) + (size_t)ct * kRec, t, idx, loc);
+                int off = 0, span = 0;
+#pragma unroll
+                for (int d = 0; d < N; ++d) {
+                    off += (int)((loc >> (kLocBits * d)) & ((1u << kLocBits) - 1u)) * stride[d];
+                    span += stride[d];
+                }
+                NINT_ASSERT(idx < E.n && (unsigned)(off + span) * sizeof(T) < G.tile_bytes);
                 const T* c = tile + off;
                 T cube[1 << N];
-                cube[0] = c[0];
-                cube[1] = c[1];
-                cube[2] = c[sy];
-                cube[3] = c[sy + 1];
-                cube[4] = c[sx];
-                cube[5] = c[sx + 1];
-                cube[6] = c[sx + sy];
-                cube[7] = c[sx + sy + 1];
+#pragma unroll
+                for (int r = 0; r < (1 << N); ++r) {  // bit (N-1-d) of r selects the upper node of axis d
+                    int o = 0;
+#pragma unroll
+                    for (int d = 0; d < N; ++d)
+                        if ((r >> (N - 1 - d)) & 1) o += stride[d];
+                    cube[r] = c[o];
+                }
                 const T value = blend_cube<T, N>(cube, t);
                 if (!(G.flags & 8u) || idx == 0xffffffffu) st_hint(E.out + idx, value, keep_pol);  // 8: measurement without the scatter
+                (void)span;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&rec_empty[st]);
-            if (++st == kEvalStages) {
+            if (++st == kStages) {
                 st = 0;
                 st_phase ^= 1u;
             }
@@ -511,9 +553,9 @@ __global__ void __launch_bounds__(kProbeThreads) order_probe2_kernel(const __gri
     }
 }
 
-// Launch interface (nint_tile_f64.cu).
+// Launch interface (nint_tile_f32.cu, nint_tile_f64.cu).
 struct TileLaunch {
-    int is_nd, all_uniform, all_analytic, sm_count;
+    int ndim, is_nd, all_uniform, all_analytic, sm_count;
     unsigned smem_bytes;  // axis pack staged by the bin kernel
     void* stream;
 };

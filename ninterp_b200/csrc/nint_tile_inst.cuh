@@ -9,9 +9,9 @@ extern std::atomic<unsigned long long> g_launch_count;
 
 namespace {
 
-template <class T, bool IS_ND, int PRE, bool UNI, bool ANA = false>
+template <class T, int N, bool IS_ND, int PRE, bool UNI, bool ANA = false>
 cudaError_t launch_bin_variant(const Params<T>& P, const TileGeom& G, const TileLaunch& cfg) {
-    auto kern = tile_bin_kernel<T, IS_ND, PRE, UNI, ANA>;
+    auto kern = tile_bin_kernel<T, N, IS_ND, PRE, UNI, ANA>;
     const unsigned smem = cfg.smem_bytes;
     if (smem > 40u * 1024u) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -36,30 +36,25 @@ cudaError_t launch_bin_variant(const Params<T>& P, const TileGeom& G, const Tile
     return cudaGetLastError();
 }
 
-template <class T, bool IS_ND, int PRE>
+template <class T, int N, bool IS_ND, int PRE>
 cudaError_t launch_bin_uni(const Params<T>& P, const TileGeom& G, const TileLaunch& cfg) {
-    if (cfg.all_uniform && cfg.all_analytic) return launch_bin_variant<T, IS_ND, PRE, true, true>(P, G, cfg);
-    return cfg.all_uniform ? launch_bin_variant<T, IS_ND, PRE, true>(P, G, cfg) : launch_bin_variant<T, IS_ND, PRE, false>(P, G, cfg);
+    if constexpr (N == 3) {  // computed nodes: the 3-D kernels only
+        if (cfg.all_uniform && cfg.all_analytic) return launch_bin_variant<T, N, IS_ND, PRE, true, true>(P, G, cfg);
+    }
+    return cfg.all_uniform ? launch_bin_variant<T, N, IS_ND, PRE, true>(P, G, cfg) : launch_bin_variant<T, N, IS_ND, PRE, false>(P, G, cfg);
 }
-template <class T, bool IS_ND>
+template <class T, int N, bool IS_ND>
 cudaError_t launch_bin_pre(const Params<T>& P, const TileGeom& G, const TileLaunch& cfg) {
-    if (P.extrap == NINT_EXTRAPOLATE_CLAMP) return launch_bin_uni<T, IS_ND, kPreClamp>(P, G, cfg);
-    if (P.extrap == NINT_EXTRAPOLATE_WRAP) return launch_bin_uni<T, IS_ND, kPreWrap>(P, G, cfg);
-    return launch_bin_uni<T, IS_ND, kPrePlain>(P, G, cfg);
+    if (P.extrap == NINT_EXTRAPOLATE_CLAMP) return launch_bin_uni<T, N, IS_ND, kPreClamp>(P, G, cfg);
+    if (P.extrap == NINT_EXTRAPOLATE_WRAP) return launch_bin_uni<T, N, IS_ND, kPreWrap>(P, G, cfg);
+    return launch_bin_uni<T, N, IS_ND, kPrePlain>(P, G, cfg);
 }
 
-}  // namespace
-
-template <>
-cudaError_t launch_tile_bin<NINT_T>(const Params<NINT_T>& P, const TileGeom& G, const TileLaunch& cfg) {
-    return cfg.is_nd ? launch_bin_pre<NINT_T, true>(P, G, cfg) : launch_bin_pre<NINT_T, false>(P, G, cfg);
-}
-
-template <>
-cudaError_t launch_tile_eval<NINT_T>(const CUtensorMap& tmap, const TileEval<NINT_T>& E, const TileGeom& G,
-                                     const TileLaunch& cfg) {
-    auto kern = tile_eval_kernel<NINT_T>;
-    const unsigned smem = 2u * G.buf_bytes + (unsigned)(kEvalStages * kEvalChunk * kTileRecBytes);
+template <class T, int N>
+cudaError_t launch_eval_n(const CUtensorMap& tmap, const TileEval<T>& E, const TileGeom& G, const TileLaunch& cfg) {
+    auto kern = tile_eval_kernel<T, N>;
+    constexpr int kRec = tile_rec_bytes<T, N>();
+    const unsigned smem = 2u * G.buf_bytes + (unsigned)(eval_stages(kRec) * kEvalChunk * kRec);
     {  // per device and function: set on every launch (a host thread may drive several GPUs)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -67,6 +62,31 @@ cudaError_t launch_tile_eval<NINT_T>(const CUtensorMap& tmap, const TileEval<NIN
     kern<<<(unsigned)cfg.sm_count, kEvalThreads, smem, (cudaStream_t)cfg.stream>>>(tmap, E, G);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
+}
+
+}  // namespace
+
+// Interp3D, and InterpND with three to five axes
+template <>
+cudaError_t launch_tile_bin<NINT_T>(const Params<NINT_T>& P, const TileGeom& G, const TileLaunch& cfg) {
+    if (!cfg.is_nd) return cfg.ndim == 3 ? launch_bin_pre<NINT_T, 3, false>(P, G, cfg) : cudaErrorInvalidValue;
+    switch (cfg.ndim) {
+    case 3: return launch_bin_pre<NINT_T, 3, true>(P, G, cfg);
+    case 4: return launch_bin_pre<NINT_T, 4, true>(P, G, cfg);
+    case 5: return launch_bin_pre<NINT_T, 5, true>(P, G, cfg);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <>
+cudaError_t launch_tile_eval<NINT_T>(const CUtensorMap& tmap, const TileEval<NINT_T>& E, const TileGeom& G,
+                                     const TileLaunch& cfg) {
+    switch (cfg.ndim) {
+    case 3: return launch_eval_n<NINT_T, 3>(tmap, E, G, cfg);
+    case 4: return launch_eval_n<NINT_T, 4>(tmap, E, G, cfg);
+    case 5: return launch_eval_n<NINT_T, 5>(tmap, E, G, cfg);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 template <>

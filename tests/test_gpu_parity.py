@@ -421,7 +421,10 @@ def test_binned_tile_route(monkeypatch):
                                                          (ND, (50, 18, 34), np.float64, "uniform", 23, 28),
                                                          (FIXED, (18, 67, 72), np.float32, "uniform", 14, 16),
                                                          (FIXED, (45, 33, 66), np.float64, "analytic", 15, 17),
-                                                         (ND, (20, 35, 40), np.float32, "analytic", 16, 28)]:
+                                                         (ND, (20, 35, 40), np.float32, "analytic", 16, 28),
+                                                         (ND, (10, 9, 12, 8), np.float64, "nonuniform", 15, 17),
+                                                         (ND, (6, 5, 7, 4, 8), np.float32, "nonuniform", 16, 18),
+                                                         (ND, (5, 4, 6, 3, 6), np.float64, "uniform", 14, 28)]:
         monkeypatch.setenv("NINT_TILE_SC_SHIFT", str(sc_shift))
         monkeypatch.setenv("NINT_TILE_SEG_SHIFT", str(seg_shift))
         # distinct cells per window of 4096 consecutive points: ~4000 (or every cell) in random order, the cells of a
@@ -432,7 +435,7 @@ def test_binned_tile_route(monkeypatch):
         for extrap in (ERROR, CLAMP, ENABLE, FILL, WRAP):
             g, o = make_pair(kind, axes, values, LIN, extrap, fill=-2.5, dtype=dtype)
             cols = _queries(rng, axes, n, dtype, 0.05)
-            for d in range(3):  # nodes (tile boundaries are nodes), their neighbours, non-finite values
+            for d in range(len(lens)):  # nodes (tile boundaries are nodes), their neighbours, non-finite values
                 a = np.asarray(axes[d], dtype=dtype)
                 special = np.concatenate([a, np.nextafter(a, dtype(np.inf)), np.nextafter(a, dtype(-np.inf)),
                                           np.array([np.nan, np.inf, -np.inf], dtype=dtype)])

@@ -86,6 +86,8 @@ def main():
     run("binned tiles", FIXED, (37, 35, 70), np.float64, LIN, ERROR, n, rng, env=tile)
     run("binned tiles wrap aos", FIXED, (40, 9, 8), np.float64, LIN, WRAP, n, rng, uniform="analytic", env=tile, aos=True)
     run("binned tiles f32 nd", ND, (21, 40, 36), np.float32, LIN, FILL, n, rng, env=tile)
+    run("binned tiles 5-d f32 wrap", ND, (6, 5, 7, 4, 8), np.float32, LIN, WRAP, n, rng, env=tile)
+    run("binned tiles 4-d f64", ND, (10, 9, 12, 8), np.float64, LIN, CLAMP, n, rng, env=tile)
     run("length-1 axes nd", ND, (1, 6, 1, 5), np.float64, LIN, CLAMP, n, rng)
     run("length-2 axes", FIXED, (2, 2, 2), np.float64, LIN, ENABLE, n, rng)
     run("1d left", FIXED, (33,), np.float64, LEFT, ERROR, n, rng)
