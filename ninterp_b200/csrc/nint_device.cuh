@@ -295,8 +295,15 @@ template <class T>
 __device__ __forceinline__ T wrap_coord(T x, T lo, T hi) {
     const T a = x - lo;
     const T b = hi - lo;
-    T r = fmod(a, b);
-    if (r < T(0)) r = r + fabs(b);
+    // fmod(a, b) is exact.  Within two spans of the grid it needs no loop: |a| < |b| leaves a, and for
+    // |b| <= |a| < 2|b| the remainder |a| - |b| is an exact subtraction (Sterbenz), with the sign of a.  NaN, inf,
+    // b == 0 and everything further out fail the test and take the library routine.
+    const T fa = fabs(a), fb = fabs(b);
+    T r;
+    if (fa < fb) r = a;
+    else if (fa < fb + fb) r = copysign(fa - fb, a);
+    else r = fmod(a, b);
+    if (r < T(0)) r = r + fb;
     return lo + r;
 }
 
@@ -858,6 +865,9 @@ constexpr int min_ctas(int n, int elem_bytes) {
 #endif
     if (n <= 2) return 4;
     if (n == 3) return 4;
+#ifdef NINT_ND_CTAS
+    if (n == 5 && elem_bytes == 4) return NINT_ND_CTAS;
+#endif
     return (n == 4 || (n == 5 && elem_bytes == 4)) ? 2 : 1;
 }
 

@@ -128,11 +128,15 @@ __device__ __forceinline__ void st_record(unsigned char* dst, const T (&t)[N], u
         for (int d = 0; d < N; ++d) w[d / 2] |= (unsigned long long)__float_as_uint((float)t[d]) << (32 * (d & 1));
     }
     w[W - 1] = (unsigned long long)idx | ((unsigned long long)loc << 32);
+    if constexpr (W % 4 == 0) {  // 32- and 64-byte records are 32-byte aligned
 #pragma unroll
-    for (int i = 0; i + 4 <= W; i += 4)
-        asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(dst + 8 * i), "l"(w[i]), "l"(w[i + 1]), "l"(w[i + 2]), "l"(w[i + 3]) : "memory");
-    if constexpr (W % 4 == 2)
-        asm volatile("st.global.v2.b64 [%0], {%1,%2};" ::"l"(dst + 8 * (W - 2)), "l"(w[W - 2]), "l"(w[W - 1]) : "memory");
+        for (int i = 0; i < W; i += 4)
+            asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(dst + 8 * i), "l"(w[i]), "l"(w[i + 1]), "l"(w[i + 2]), "l"(w[i + 3]) : "memory");
+    } else {  // 48-byte records: 16-byte aligned
+#pragma unroll
+        for (int i = 0; i < W; i += 2)
+            asm volatile("st.global.v2.b64 [%0], {%1,%2};" ::"l"(dst + 8 * i), "l"(w[i]), "l"(w[i + 1]) : "memory");
+    }
 }
 // from a record stage in shared memory
 template <class T, int N>
@@ -163,7 +167,10 @@ __device__ __forceinline__ void ld_record_shared(const unsigned char* src, T (&t
 #define NINT_BIN_ANA_CTAS 4  // resident CTAs the analytic variant is compiled for; 5 (48 registers) and 6 (40) spill and
                             // measured slower: 16.3 -> 19.1 and 19.5 ms per 1e9 points
 #endif
-constexpr int bin_ctas(int n, bool ana) { return n == 3 ? (ana ? NINT_BIN_ANA_CTAS : 4) : 2; }
+#ifndef NINT_BIN_ND_CTAS
+#define NINT_BIN_ND_CTAS 4  // four and five axes: the weights need no corner registers, the rare overflow gather may spill
+#endif
+constexpr int bin_ctas(int n, bool ana) { return n == 3 ? (ana ? NINT_BIN_ANA_CTAS : 4) : NINT_BIN_ND_CTAS; }
 
 template <class T, int N, bool IS_ND, int PRE, bool UNI, bool ANA = false>
 __global__ void __launch_bounds__(kBlock, bin_ctas(N, ANA)) tile_bin_kernel(const __grid_constant__ Params<T> P,
