@@ -659,6 +659,10 @@ bool tile_route(const nint_handle* h, size_t n, int windows) {
     // single pass 50.6 ms.  So the slab passes keep the batches they can take, and the binned tiles take the ones
     // they cannot: Extrapolate::Wrap, which re-maps coordinates across axes.
     if (windows > 0 && !forced) return false;
+    // Four and five axes: measured slower than the single pass (InterpND f32 32^5 under Wrap, 2e8 points: bin 15.2 ms +
+    // evaluate 13 ms against 22 ms).  There the front-end (five non-uniform axes, wrap) costs ~800 instructions per point
+    // and is paid by the bin kernel again, and tiles that fit shared memory carry 3.3x halo.  Offered with NINT_ROUTE=tile.
+    if (h->ndim_eff > 3 && !forced) return false;
     for (int d = 0; d < h->ndim_eff; ++d)
         if (!(h->ax[d].flags & nint::kAxisFast)) return false;
     const char* e_bytes = std::getenv("NINT_SLAB_MIN_BYTES");

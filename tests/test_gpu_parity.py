@@ -413,6 +413,7 @@ def test_binned_tile_route(monkeypatch):
     monkeypatch.setenv("NINT_SLAB_MIN_POINTS", "0")
     monkeypatch.setenv("NINT_ROUTE", "tile")
     monkeypatch.setenv("NINT_PROBE_SHIFT", "0")
+    monkeypatch.setenv("NINT_COMPACT", "0")  # 4-D / 5-D Fill and Error batches would otherwise take the in-range compaction pass
     rng = np.random.default_rng(4242)
     n = 300_001
     for kind, lens, dtype, mode, sc_shift, seg_shift in [(FIXED, (40, 9, 8), np.float64, "uniform", 16, 17),
