@@ -5,6 +5,7 @@ mkdir -p gpurun_out
 P="python tools/prof_case.py"
 cap() {  # name, kernel regex, count, command...
   local name=$1 regex=$2 count=$3; shift 3
+  if [ -n "$ONLY" ] && ! echo " $ONLY " | grep -q " $name "; then return; fi
   "$@" > gpurun_out/r2p_plain_$name.log 2>&1 &&
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$regex -c $count -o /tmp/r2p_$name "$@" > gpurun_out/r2p_ncu_$name.log 2>&1
   echo "$name rc=$?"
@@ -14,15 +15,16 @@ cap() {  # name, kernel regex, count, command...
   rm -f /tmp/r2p_$name.ncu-rep /tmp/r2p_src_$name.csv
 }
 cap slab "slab_kernel" 3 $P --case random --points 1e9 --launches 1
-cap sorted "interp_kernel" 1 $P --case sorted --points 1e9 --launches 1
-cap tilesorted "interp_kernel" 1 $P --case tilesorted --points 1e9 --launches 1
+cap sorted "interp_pipe_kernel" 1 $P --case sorted --points 1e9 --launches 1
+cap tilesorted "interp_pipe_kernel" 1 $P --case tilesorted --points 1e9 --launches 1
 cap tiles "tile_" 2 env NINT_ROUTE=tile $P --case random --points 2.6e8 --launches 1
 cap fused1d "interp1d_fused" 1 $P --case 1d --points 4e8 --launches 1
 cap nd5fill "slab_kernel" 1 $P --case nd5 --extrap fill --points 2e8 --launches 1
 cap nd5wrap "interp_kernel" 1 $P --case nd5 --points 2e8 --launches 1
 cap near2d "interp_kernel" 1 $P --case 2d --strategy nearest --points 1e8 --launches 1
 cap lin2d "interp_kernel" 1 $P --case 2d --points 1e8 --launches 1
-python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/r2p_bench_plain.log 2>&1 &&
+[ -n "$ONLY" ] || python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/r2p_bench_plain.log 2>&1 &&
+[ -n "$ONLY" ] ||
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2p_bench_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/r2p_bench_ncu.log 2>&1
 echo "bench launch list rc=$?"
 du -sh gpurun_out
