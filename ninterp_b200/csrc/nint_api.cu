@@ -997,9 +997,11 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     P.mode_flag = flag;
     P.mode_want = nint::kModeCoherent;
     P.blocked = std::getenv("NINT_NO_BLOCKED") ? 0 : 1;
+    P.wide_lines = std::getenv("NINT_NO_WIDE") ? 0 : 1;
     e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : launch_single_pass<T>(h, P, cfg, pipe_mode != 0);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     P.blocked = 0;
+    P.wide_lines = 0;
     P.mode_want = nint::kModeRandom;
     if (tile) {
         const int rc = launch_tiles<T>(h, P, cfg, stream);

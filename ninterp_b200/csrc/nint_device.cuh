@@ -92,6 +92,7 @@ struct Params {
     const int* mode_flag;
     int mode_want;
     int blocked;  // interp_kernel: every CTA walks one contiguous range of the batch instead of striding over it
+    int wide_lines;  // coherent batches: the cell-packed table is read with an L2 prefetch size of 256 bytes
     T win_lo_x, win_hi_x;
     int win_first, win_last;
     int L[kMaxDim];
@@ -186,6 +187,33 @@ __device__ __forceinline__ void ld_table2(const float* p, unsigned long long pol
 
 // One cell of the cell-packed table: COUNT = 2^N contiguous elements, loaded 32 bytes at a time (LDG.256 on
 // sm_100) or with the widest load the block size allows; plain LRU, no cache-policy operand.
+// The same with an L2 prefetch-size hint of 256 bytes: on batches the order probe found coherent the neighbouring cells'
+// blocks are the next ones needed, and a first touch then brings four 64-byte blocks into L2 for one DRAM round trip.
+template <int COUNT>
+__device__ __forceinline__ void ld_cells_wide(const double* p, double (&v)[COUNT]) {
+    if constexpr (COUNT >= 4) {
+#pragma unroll
+        for (int k = 0; k < COUNT; k += 4)
+            asm volatile("ld.global.nc.L2::256B.v4.f64 {%0,%1,%2,%3}, [%4];"
+                         : "=d"(v[k]), "=d"(v[k + 1]), "=d"(v[k + 2]), "=d"(v[k + 3]) : "l"(p + k));
+    } else {
+        asm volatile("ld.global.nc.L2::256B.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+    }
+}
+template <int COUNT>
+__device__ __forceinline__ void ld_cells_wide(const float* p, float (&v)[COUNT]) {
+    if constexpr (COUNT >= 8) {
+#pragma unroll
+        for (int k = 0; k < COUNT; k += 8)
+            asm volatile("ld.global.nc.L2::256B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(v[k]), "=f"(v[k + 1]), "=f"(v[k + 2]), "=f"(v[k + 3]), "=f"(v[k + 4]), "=f"(v[k + 5]),
+                           "=f"(v[k + 6]), "=f"(v[k + 7]) : "l"(p + k));
+    } else if constexpr (COUNT == 4) {
+        asm volatile("ld.global.nc.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+    } else {
+        asm volatile("ld.global.nc.L2::256B.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "l"(p));
+    }
+}
 template <int COUNT>
 __device__ __forceinline__ void ld_cells(const double* p, double (&v)[COUNT]) {
     if constexpr (COUNT >= 4) {
@@ -787,7 +815,8 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
 #pragma unroll
             for (int d = 0; d < N; ++d) cell += (unsigned)k[d] * (unsigned)P.cstride[d];
             NINT_ASSERT((unsigned long long)cell < P.ncells);
-            ld_cells<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
+            if (P.wide_lines) ld_cells_wide<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
+            else ld_cells<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
         } else {
             long long base = 0;
             long long step[N];
