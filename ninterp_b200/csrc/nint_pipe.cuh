@@ -10,7 +10,9 @@
 // Every CTA walks one contiguous range of chunks.
 //
 // Measured on B200 (1e9 points, 256^3 f64): cell-ordered 143 -> 146 Gpoints/s, Morton order 144 -> 151, queries grouped
-// by 8^3-cell tiles 84 -> 89, f32 cell-ordered 178 -> 187.  The gain is small because the wait moves: with the
+// by 8^3-cell tiles 84 -> 89, f32 cell-ordered 178 -> 187.  (Once the table loads carried a 256-byte L2 prefetch size the
+// two kernels ended within 3 % of each other -- the ring couples the CTA's 16 warps, and ncu shows the consumers
+// spinning on chunks a slower warp still holds back -- and the default became: pipelined for f32, interp_kernel for f64.)  The gain is small because the wait moves: with the
 // coordinates on time a warp still meets, on nearly every trip, a cell nobody has touched yet and waits a DRAM round
 // trip for its corner block (32 warps x 32 points per ~1 us and SM = 145 Gpoints/s).  Tried against that and dropped:
 // a 17th warp that guesses the cells of the chunks in flight and requests their lines -- with prefetch.global the
