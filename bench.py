@@ -197,9 +197,13 @@ def _cpu_model():
 
 def _git_head():
     try:
-        return subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT, capture_output=True, text=True).stdout.strip() or None
+        head = subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT, capture_output=True, text=True).stdout.strip()
     except Exception:
-        return None
+        head = ""
+    if head:
+        return head
+    stamp = ROOT / "ninterp_b200" / "_build" / "commit"  # written by ninterp_b200.build where .git exists (not on the GPU box)
+    return stamp.read_text().strip() if stamp.exists() else None
 
 
 def kernel_source_sha():

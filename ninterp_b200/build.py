@@ -49,7 +49,23 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
+def _record_commit() -> None:
+    """Leaves the commit the library was built at beside the objects: the GPU box gets a snapshot without .git, and
+    bench.py stamps its JSON line from this file there."""
+    try:
+        root = PKG.parent
+        head = subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=root, capture_output=True, text=True).stdout.strip()
+        if not head:
+            return
+        dirty = subprocess.run(["git", "status", "--porcelain", "--untracked-files=no"], cwd=root, capture_output=True, text=True).stdout.strip()
+        OBJ.mkdir(exist_ok=True)
+        (OBJ / "commit").write_text(head + ("+dirty" if dirty else ""))
+    except Exception:
+        pass
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
+    _record_commit()
     stamp_file = OBJ / "stamp"
     stamp = _stamp()
     if not force and SO.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:

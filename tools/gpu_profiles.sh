@@ -15,8 +15,8 @@ cap() {  # name, kernel regex, count, command...
   rm -f /tmp/r2p_$name.ncu-rep /tmp/r2p_src_$name.csv
 }
 cap slab "slab_kernel" 3 $P --case random --points 1e9 --launches 1
-cap sorted "interp_pipe_kernel" 1 $P --case sorted --points 1e9 --launches 1
-cap tilesorted "interp_pipe_kernel" 1 $P --case tilesorted --points 1e9 --launches 1
+cap sorted "interp_kernel" 1 $P --case sorted --points 1e9 --launches 1
+cap tilesorted "interp_kernel" 1 $P --case tilesorted --points 1e9 --launches 1
 cap tiles "tile_" 2 env NINT_ROUTE=tile $P --case random --points 2.6e8 --launches 1
 cap fused1d "interp1d_fused" 1 $P --case 1d --points 4e8 --launches 1
 cap nd5fill "slab_kernel" 1 $P --case nd5 --extrap fill --points 2e8 --launches 1

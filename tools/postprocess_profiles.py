@@ -39,7 +39,7 @@ def main():
             continue
         plain = (out / f"r2p_plain_{key}.log").read_text().strip().splitlines()
         text = [f"# ncu --set full --clock-control none --import-source on, B200, round 2, captured at commit {commit} (tools/gpu_profiles.sh)",
-                f"# event-timed run of the same command (not under ncu): {plain[-1] if plain else '?'}", summ.read_text(), "",
+                f"# event-timed run of the same command, not under ncu (ONE cold launch incl. first-call setup; bench.py holds the warmed numbers): {plain[-1] if plain else "?"}", summ.read_text(), "",
                 "## source page (tools/ncu_source.py): memory instructions and top stall sites", (out / f"r2p_source_{key}.txt").read_text()]
         (prof / f"r2_ncu_full_{name}.txt").write_text("\n".join(text))
     # launch list of the bench command
