@@ -425,12 +425,12 @@ def bits_checksum(torch, out):
 
 
 def routes_checksum(torch, interp, cols, out, status=None):
-    """The same batch through every route the library has for it (binned tiles, slab passes, single pass):
-    the result bits must not depend on the route."""
+    """The same batch through every route the library has for it (slab lists, binned tiles, slab passes, single
+    pass): the result bits must not depend on the route."""
     sums = {}
     saved = {k: os.environ.get(k) for k in ("NINT_ROUTE",)}
     try:
-        for route in ("tile", "slab", "single"):
+        for route in ("part", "tile", "slab", "single"):
             os.environ["NINT_ROUTE"] = route
             out.zero_()
             interp.interpolate_batch(cols, out=out, status=status)
@@ -483,7 +483,7 @@ def run_b200(args, rank, local_rank, world):
     launches_rank = int(time_steps.launches)
     launches = torch.tensor([launches_rank], dtype=torch.int64, device=dev)
     order = int(lib.nint_last_query_order(interp._h))  # 0 no probe, 1 coherent, 2 incoherent
-    route = int(lib.nint_last_incoherent_route(interp._h)) if order == 2 else 0  # 1 slab passes, 2 binned tiles
+    route = int(lib.nint_last_incoherent_route(interp._h)) if order == 2 else 0  # 1 slab passes, 2 binned tiles, 3 slab lists
     if world > 1:
         dist.all_reduce(launches)
     value = n_total * args.steps / secs / 1e9
@@ -497,8 +497,8 @@ def run_b200(args, rank, local_rank, world):
     traffic, traffic_note = None, None
     try:
         tj = json.load(open(ROOT / "profiles" / "traffic.json"))
-        key = {2: "interp3d_linear_f64_uniform_random_tiles_bytes_per_call", 1: "interp3d_linear_f64_uniform_random_slab_bytes_per_call"}.get(
-            route, "interp3d_linear_f64_uniform_random_bytes_per_launch")
+        key = {3: "interp3d_linear_f64_uniform_random_lists_bytes_per_call", 2: "interp3d_linear_f64_uniform_random_tiles_bytes_per_call",
+               1: "interp3d_linear_f64_uniform_random_slab_bytes_per_call"}.get(route, "interp3d_linear_f64_uniform_random_bytes_per_launch")
         traffic = tj.get(key)
         if traffic is not None and world > 1:
             traffic = traffic * n / 1e9  # the capture is of a 1e9-point call; a rank's share scales with its points
@@ -507,7 +507,8 @@ def run_b200(args, rank, local_rank, world):
                         "stale": tj.get("kernel_source_sha") != kernel_source_sha()}
     except Exception:
         pass
-    kernel_name = {2: f"order_probe2_kernel + {(per_call - 2) // 2} x (tile_bin_kernel<double,...> + tile_eval_kernel<double>) per batch call",
+    kernel_name = {3: f"order_probe2_kernel + {(per_call - 2) // 3} x (part_scatter_kernel<double> + part_eval_kernel<double,...> + part_merge_kernel<double>) per batch call",
+                   2: f"order_probe2_kernel + {(per_call - 2) // 2} x (tile_bin_kernel<double,...> + tile_eval_kernel<double>) per batch call",
                    1: f"order_probe2_kernel + {per_call - 2} x slab_kernel<double,3,...> per batch call"}.get(
         route, "interp_kernel<double,3,fixed,Linear,smem,plain,uniform>")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -552,8 +553,8 @@ def run_b200(args, rank, local_rank, world):
         status = torch.empty(n, dtype=torch.uint8, device=dev)
         variants["random_queries_with_status_mask"] = timed(interp, cols, out, status=status, bpp=33, oracle=o3, sample=16_000_000)
         del status
-        # cfg 3 forced onto the other routes, for the record: binned tiles (TMA-staged, nint_tile.cuh) and the single pass
-        for name, route_env in (("random_queries_binned_tiles", "tile"), ("random_queries_single_pass", "single")):
+        # cfg 3 forced onto the other routes, for the record: slab passes, binned tiles (TMA-staged, nint_tile.cuh), single pass
+        for name, route_env in (("random_queries_slab_passes", "slab"), ("random_queries_binned_tiles", "tile"), ("random_queries_single_pass", "single")):
             os.environ["NINT_ROUTE"] = route_env
             variants[name] = timed(interp, cols, out, steps=5)
             os.environ.pop("NINT_ROUTE", None)

@@ -22,7 +22,7 @@ VARIANT = os.environ.get("NINT_LIB_VARIANT", "")
 OBJ = PKG / ("_build" + ("_" + VARIANT if VARIANT else ""))
 SO = PKG / ("libninterp_cuda" + ("_" + VARIANT if VARIANT else "") + ".so")
 
-SOURCES = ["nint_api.cu", "nint_fixed_f64.cu", "nint_fixed_f32.cu", "nint_nd_f64.cu", "nint_nd_f32.cu", "nint_tile_f64.cu", "nint_tile_f32.cu", "nint_selftest.cu"]
+SOURCES = ["nint_api.cu", "nint_fixed_f64.cu", "nint_fixed_f32.cu", "nint_nd_f64.cu", "nint_nd_f32.cu", "nint_tile_f64.cu", "nint_tile_f32.cu", "nint_part_f64.cu", "nint_part_f32.cu", "nint_selftest.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -19,6 +19,7 @@
 #include <thread>
 #include <vector>
 
+#include "nint_part.cuh"
 #include "nint_tile.cuh"
 
 namespace nint {
@@ -139,7 +140,7 @@ struct nint_handle {
     nint::ProbeSlot* d_probe = nullptr;  // ring of order-probe slots (verdict + scratch), one per batch call
     std::atomic<unsigned> mode_slot{0};
     std::atomic<const int*> last_mode{nullptr};  // verdict of the most recent batch if it was probed (diagnostics)
-    std::atomic<int> last_route{0};              // what was enqueued for an incoherent verdict: 0 none, 1 slab passes, 2 binned tiles
+    std::atomic<int> last_route{0};              // what was enqueued for an incoherent verdict: 0 none, 1 slab passes, 2 binned tiles, 3 slab lists
     int probe_shift = 3;                         // log2(cells per coarse tile and axis) of the order probe
     unsigned probe_max_distinct = 0;             // coherent when the windows' mean footprint is at most this many coarse tiles
     // binned route (nint_tile.cuh): tile geometry, TMA descriptor of the plain table, pool for the per-call lists
@@ -680,6 +681,24 @@ bool tile_route(const nint_handle* h, size_t n, int windows) {
     return true;
 }
 
+// The stream-ordered pool the per-call lists of the binned tiles and the slab lists come from.
+bool ensure_pool(nint_handle* h) {
+    if (h->pool) return true;
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = h->device;
+    if (cudaMemPoolCreate(&h->pool, &props) != cudaSuccess) {
+        cudaGetLastError();
+        h->pool = nullptr;
+        return false;
+    }
+    unsigned long long keep = ~0ull;  // the lists are the same size call after call: keep them in the pool
+    cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    return true;
+}
+
 // TMA descriptor of the plain table and the tile geometry.  Not an error when it cannot be built (strides that are
 // not 16-byte multiples, no driver entry point): the route is simply not offered.
 void build_tile(nint_handle* h) {
@@ -784,20 +803,7 @@ void build_tile(nint_handle* h) {
                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,  // box rows are short (272 B in 3-D f64): promoted to 256 B they fetch 512
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return;
-    if (!h->pool) {
-        cudaMemPoolProps props{};
-        props.allocType = cudaMemAllocationTypePinned;
-        props.handleTypes = cudaMemHandleTypeNone;
-        props.location.type = cudaMemLocationTypeDevice;
-        props.location.id = h->device;
-        if (cudaMemPoolCreate(&h->pool, &props) != cudaSuccess) {
-            cudaGetLastError();
-            h->pool = nullptr;
-            return;
-        }
-        unsigned long long keep = ~0ull;  // the lists are the same size call after call: keep them in the pool
-        cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
+    if (!ensure_pool(h)) return;
     h->tile_ready = true;
 }
 
@@ -880,6 +886,111 @@ int launch_tiles(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
         if (e != cudaSuccess) rc = cuda_fail(e, "binned route launch");
     }
     (void)es;
+    cudaFreeAsync(scratch, stream);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------- slab lists (nint_part.cuh)
+// Number of lists (slabs of the cell-packed table along axis 0) an incoherent batch of n points is split into; 0 = the
+// route does not apply.  Same regime as the slab passes (3-D Linear, axes staged in shared memory, a packed table the
+// single pass cannot keep in L2, a batch large enough), any Extrapolate policy.  NINT_ROUTE=part forces the route where
+// it applies, NINT_ROUTE=slab|tile|single and NINT_SLABS exclude it; NINT_PART_SLAB_MB sets the slab size.
+int part_lists(const nint_handle* h, size_t n, int* cells_per_list) {
+    if (h->constant || h->ndim_eff != 3 || h->strategy != NINT_LINEAR || !h->smem_axes || !h->d_cells) return 0;
+    const char* route = std::getenv("NINT_ROUTE");
+    const bool forced = route && !std::strcmp(route, "part");
+    if (route && !forced) return 0;
+    if (std::getenv("NINT_SLABS") && !forced) return 0;
+    // Measured on B200 (256^3, 1e9 random points; slab lists vs slab passes): uniform axes 25.6 vs 30.6 ms (f64, nodes
+    // computed), 28.3 vs 30.6 ms (f64, nodes loaded), 17.4 vs 19.3 ms (f32); non-uniform axes 36.5 vs 35.7 ms.  So
+    // the lists take the interpolators whose axes are all uniform; the others keep the slab passes / binned tiles.
+    for (int d = 0; d < h->ndim_eff && !forced; ++d)
+        if ((h->ax[d].flags & (nint::kAxisUniform | nint::kAxisFast)) != (nint::kAxisUniform | nint::kAxisFast)) return 0;
+    const char* e_bytes = std::getenv("NINT_SLAB_MIN_BYTES");
+    const char* e_points = std::getenv("NINT_SLAB_MIN_POINTS");
+    const long long min_bytes = e_bytes ? std::atoll(e_bytes) : 256ll << 20;
+    const long long min_points = e_points ? std::atoll(e_points) : 1ll << 22;
+    if ((long long)n < min_points) return 0;
+    const double packed = (double)h->ncells * 8.0 * (double)elem_size(h->dtype);
+    if (packed < (double)min_bytes) return 0;
+    const char* e_mb = std::getenv("NINT_PART_SLAB_MB");
+    const double slab = (e_mb ? std::atof(e_mb) : 40.0) * 1024.0 * 1024.0;
+    const int cells0 = (int)h->axis_len[0] - 1;
+    const double plane = packed / (double)cells0;  // bytes of the packed table per axis-0 cell
+    int per = std::max(1, (int)std::floor(slab / plane));
+    int lists = (cells0 + per - 1) / per;
+    if (lists < 2 || lists > nint::kPartMaxLists) return 0;
+    *cells_per_list = per;
+    return lists;
+}
+
+// Enqueues scatter + evaluate + merge for the whole launch, in segments whose lists fit the scratch budget.
+// NINT_E_UNSUPPORTED: no memory for the lists (nothing was enqueued for the incoherent verdict yet).
+template <class T>
+int launch_parts(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, int lists, int per, cudaStream_t stream) {
+    if (!ensure_pool(h)) return NINT_E_UNSUPPORTED;
+    unsigned seg_shift = 28;
+    if (const char* env = std::getenv("NINT_PART_SEG_SHIFT")) seg_shift = (unsigned)std::atoi(env);
+    seg_shift = std::min(30u, std::max(nint::kPartChunkShift, seg_shift));
+    const unsigned long long seg = 1ull << seg_shift;
+    const unsigned long long n = P.n;
+    const unsigned long long cap = (std::min(n, seg) + nint::kPartChunk - 1) / nint::kPartChunk * nint::kPartChunk;
+    const unsigned max_chunks = (unsigned)(cap / nint::kPartChunk);
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t col = up((size_t)cap * sizeof(T));
+    const size_t bytes = 4 * col + up((size_t)cap) + up((size_t)cap * 2) + up((size_t)lists * max_chunks * sizeof(unsigned)) + 256;
+    unsigned char* scratch = nullptr;
+    if (cudaMallocFromPoolAsync((void**)&scratch, bytes, h->pool, stream) != cudaSuccess) {
+        cudaGetLastError();
+        return NINT_E_UNSUPPORTED;
+    }
+    nint::PartGeom<T> G{};
+    G.lists = lists;
+    G.uniform = (h->ax[0].flags & nint::kAxisUniform) ? 1 : 0;
+    G.wrap = h->extrap == NINT_EXTRAPOLATE_WRAP;
+    const T* g0 = (const T*)h->axes_host[0].data();
+    const int cells0 = (int)h->axis_len[0] - 1;
+    G.x0 = g0[0];
+    G.x1 = g0[cells0];
+    G.scale = (T)(h->ax[0].inv_h / (double)per);
+    for (int k = 0; k < nint::kPartMaxLists; ++k) G.thr[k] = g0[std::min(cells0, k * per)];
+    unsigned char* q = scratch;
+    for (int d = 0; d < 3; ++d, q += col) G.rec[d] = (T*)q;
+    G.vals = (T*)q;
+    q += col;
+    G.stat = q;
+    q += up((size_t)cap);
+    G.pos = (unsigned short*)q;
+    q += up((size_t)cap * 2);
+    G.runs = (unsigned*)q;
+    q += up((size_t)lists * max_chunks * sizeof(unsigned));
+    G.ticket = (unsigned*)q;
+    G.run_stride = max_chunks;
+    nint::PartLaunch pl;
+    pl.is_nd = cfg.is_nd;
+    pl.all_uniform = cfg.all_uniform;
+    pl.all_analytic = std::getenv("NINT_NO_ANALYTIC") ? 0 : 1;
+    for (int d = 0; d < 3; ++d)
+        if (!(h->ax[d].flags & nint::kAxisAnalytic)) pl.all_analytic = 0;
+    pl.sm_count = cfg.sm_count;
+    pl.smem_bytes = cfg.smem_bytes;
+    pl.stream = stream;
+    const T* cols0[3] = {P.coords[0], P.coords[1], P.coords[2]};
+    T* out0 = P.out;
+    uint8_t* st0 = P.status;
+    const unsigned long long base0 = P.index_base;
+    int rc = NINT_OK;
+    for (unsigned long long start = 0; start < n && rc == NINT_OK; start += seg) {
+        const unsigned long long m = std::min(seg, n - start);
+        for (int d = 0; d < 3; ++d) P.coords[d] = cols0[d] + start * P.coord_stride;
+        P.out = out0 + start;
+        P.status = st0 ? st0 + start : nullptr;
+        P.n = m;
+        P.index_base = base0 + start;
+        G.nchunks = (unsigned)((m + nint::kPartChunk - 1) / nint::kPartChunk);
+        const cudaError_t e = nint::launch_part<T>(P, G, pl);
+        if (e != cudaSuccess) rc = cuda_fail(e, "slab-list route launch");
+    }
     cudaFreeAsync(scratch, stream);
     return rc;
 }
@@ -967,6 +1078,8 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     // against 0.2 ms of single pass): no order probe, no multi-launch routes there.
     int windows = pipeline_chunk ? 0 : slab_windows(h, n);
     const bool tile = pipeline_chunk ? false : tile_route(h, n, windows);
+    int part_per = 0;
+    const int parts = pipeline_chunk ? 0 : part_lists(h, n, &part_per);
     h->last_route.store(0, std::memory_order_relaxed);
     // InterpND with four or more axes under Fill or Error: one pass that compacts the in-range points first (see
     // slab_kernel<INR>); NINT_COMPACT=0 keeps the plain single pass
@@ -982,7 +1095,7 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
         if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
         return NINT_OK;
     }
-    if (windows <= 0 && !tile) {
+    if (windows <= 0 && !tile && parts <= 0) {
         h->last_mode.store(nullptr, std::memory_order_relaxed);
         cudaError_t e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : launch_single_pass<T>(h, P, cfg, pipe_mode == 1);
         if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
@@ -1006,6 +1119,20 @@ int launch_typed(nint_handle* h, const void* const* cols, long long coord_stride
     P.blocked = 0;
     P.wide_lines = 0;
     P.mode_want = nint::kModeRandom;
+    if (parts > 0) {
+        const int rc = launch_parts<T>(h, P, cfg, parts, part_per, stream);
+        if (rc == NINT_OK) {
+            h->last_route.store(3, std::memory_order_relaxed);
+            return NINT_OK;
+        }
+        if (rc != NINT_E_UNSUPPORTED) return rc;
+        if (windows <= 0 && !tile) {  // no memory for the lists and no other route: the single pass takes both verdicts
+            cfg.slab = 0;
+            e = cfg.is_nd ? nint::launch_nd<T>(P, cfg) : nint::launch_fixed<T>(P, cfg);
+            if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+            return NINT_OK;
+        }
+    }
     if (tile) {
         const int rc = launch_tiles<T>(h, P, cfg, stream);
         if (rc == NINT_OK) {

@@ -240,6 +240,25 @@ __device__ __forceinline__ void ld_cells(const float* p, float (&v)[COUNT]) {
     }
 }
 
+// The same with an L2 cache policy (the slab lists keep the slab being gathered from evict_last: nint_part.cuh).
+template <int COUNT>
+__device__ __forceinline__ void ld_cells_keep(const double* p, unsigned long long pol, double (&v)[COUNT]) {
+    static_assert(COUNT >= 4, "3-D cells");
+#pragma unroll
+    for (int k = 0; k < COUNT; k += 4)
+        asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=d"(v[k]), "=d"(v[k + 1]), "=d"(v[k + 2]), "=d"(v[k + 3]) : "l"(p + k), "l"(pol));
+}
+template <int COUNT>
+__device__ __forceinline__ void ld_cells_keep(const float* p, unsigned long long pol, float (&v)[COUNT]) {
+    static_assert(COUNT >= 8, "3-D cells");
+#pragma unroll
+    for (int k = 0; k < COUNT; k += 8)
+        asm volatile("ld.global.nc.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                     : "=f"(v[k]), "=f"(v[k + 1]), "=f"(v[k + 2]), "=f"(v[k + 3]), "=f"(v[k + 4]), "=f"(v[k + 5]),
+                       "=f"(v[k + 6]), "=f"(v[k + 7]) : "l"(p + k), "l"(pol));
+}
+
 // Two adjacent table elements row[0], row[1] with one aligned vector load; when `row` sits in the upper
 // half of its aligned pair a second (predicated) vector load fetches the neighbour.  The table is
 // allocated with one pair of slack so the neighbour load never leaves the allocation.
@@ -707,7 +726,9 @@ __device__ __forceinline__ bool fast_weights_analytic(const Params<T>& P, const 
 }
 
 // The whole fast path for one point; false when anything about it needs the general path.
-template <class T, int N, bool IS_ND, int STRAT, bool UNI, bool FIRST, bool PLAIN = false, bool ANA = false>
+// PLAIN: 0 = Linear gathers from the cell-packed table when there is one, 1 = from the plain table (slab passes),
+// 2 = from the cell-packed table with the L2 policy `pol` (slab lists; 3-D only)
+template <class T, int N, bool IS_ND, int STRAT, bool UNI, bool FIRST, int PLAIN = 0, bool ANA = false>
 __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned char* pack, unsigned long long pol,
                                            const T (&p)[N], T& result) {
     constexpr bool kCollapse = IS_ND || (N == 1);
@@ -718,12 +739,13 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
         ok = fast_weights_analytic<T, N, IS_ND, FIRST>(P, p, k, t);
         if (N >= 4 && !ok) return false;
         T cube[1 << N];
-        if (!PLAIN && P.cells != nullptr) {
+        if (PLAIN != 1 && P.cells != nullptr) {
             unsigned cell = 0;
 #pragma unroll
             for (int d = 0; d < N; ++d) cell += (unsigned)k[d] * (unsigned)P.cstride[d];
             NINT_ASSERT((unsigned long long)cell < P.ncells);
-            ld_cells<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
+            if constexpr (PLAIN == 2 && N == 3) ld_cells_keep<(1 << N)>(P.cells + (size_t)cell * (1 << N), pol, cube);
+            else ld_cells<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
         } else {
             long long base = 0;
             long long step[N];
@@ -810,13 +832,17 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
         if (N >= 4 && !ok) return false;
         T cube[1 << N];
         // the all-uniform kernels are only dispatched when the cell-packed table exists (nint_launch.cuh)
-        if (!PLAIN && (UNI || P.cells != nullptr)) {
+        if (PLAIN != 1 && (UNI || P.cells != nullptr)) {
             unsigned cell = 0;  // build_cells() only packs tables with fewer than 2^31 cells
 #pragma unroll
             for (int d = 0; d < N; ++d) cell += (unsigned)k[d] * (unsigned)P.cstride[d];
             NINT_ASSERT((unsigned long long)cell < P.ncells);
-            if (P.wide_lines) ld_cells_wide<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
-            else ld_cells<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
+            if constexpr (PLAIN == 2 && N == 3) {
+                ld_cells_keep<(1 << N)>(P.cells + (size_t)cell * (1 << N), pol, cube);
+            } else {
+                if (P.wide_lines) ld_cells_wide<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
+                else ld_cells<(1 << N)>(P.cells + (size_t)cell * (1 << N), cube);
+            }
         } else {
             long long base = 0;
             long long step[N];

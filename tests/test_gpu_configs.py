@@ -56,7 +56,7 @@ def test_config3_interp3d_linear_256cubed():
 
     from ninterp_b200 import _lib
 
-    for axes in ([np.arange(256) * (1.0 / 255)] * 3, [np.cumsum(rng.uniform(0.5, 1.5, 256)) for _ in range(3)]):
+    for axes, route in (([np.arange(256) * (1.0 / 255)] * 3, 3), ([np.cumsum(rng.uniform(0.5, 1.5, 256)) for _ in range(3)], 1)):
         # 6e6 points: above the batch size from which a table of this size is routed by the order probe
         cols = [rng.uniform(a[0], a[-1], 6_000_000) for a in axes]
         g, o = make_pair(0, axes, v, LIN, ERROR, dtype=np.float64)
@@ -65,7 +65,8 @@ def test_config3_interp3d_linear_256cubed():
         assert_same(got, st, want, st_want, "random order")
         assert info == expected_info(st_want) and (st == 0).all()
         assert _lib.lib().nint_last_query_order(g._h) == 2  # incoherent ...
-        assert _lib.lib().nint_last_incoherent_route(g._h) == 1  # ... slab passes over the plain table
+        # ... slab lists on the cell-packed table (uniform axes) or slab passes over the plain table (non-uniform)
+        assert _lib.lib().nint_last_incoherent_route(g._h) == route
         # cell-sorted order must give the same values as the unsorted batch, through the single pass
         order = np.lexsort([np.searchsorted(axes[2], cols[2]), np.searchsorted(axes[1], cols[1]),
                             np.searchsorted(axes[0], cols[0])])
@@ -74,23 +75,25 @@ def test_config3_interp3d_linear_256cubed():
         assert _lib.lib().nint_last_query_order(g._h) == 1
 
 
-def test_config3_wrap_takes_the_binned_tiles():
+def test_config3_wrap_routes():
     # the same table under Extrapolate::Wrap (coordinates are re-mapped across axes, so the slab passes do not apply):
-    # incoherent batches are bucketed by grid tile and evaluated from TMA-staged tiles in shared memory
+    # uniform axes take the slab lists (points are classified by their wrapped axis-0 coordinate); non-uniform axes are
+    # bucketed by grid tile and evaluated from TMA-staged tiles in shared memory
     from gpu_util import assert_same, expected_info, gpu_eval, make_pair
 
     from ninterp_b200 import _lib
 
     rng = np.random.default_rng(33)
     v = rng.uniform(0, 1, (256, 256, 256))
-    axes = [np.arange(256) * (1.0 / 255)] * 3
-    cols = [rng.uniform(-0.3, 1.3, 6_000_000) for _ in axes]
-    g, o = make_pair(0, axes, v, LIN, WRAP, dtype=np.float64)
-    want, st_want = o.eval(cols, nthreads=O.max_threads())
-    got, st, info = gpu_eval(g, cols)
-    assert_same(got, st, want, st_want, "wrap, random order")
-    assert info == expected_info(st_want)
-    assert _lib.lib().nint_last_query_order(g._h) == 2 and _lib.lib().nint_last_incoherent_route(g._h) == 2
+    for axes, route in (([np.arange(256) * (1.0 / 255)] * 3, 3), ([np.cumsum(rng.uniform(0.5, 1.5, 256)) for _ in range(3)], 2)):
+        span = [a[-1] - a[0] for a in axes]
+        cols = [rng.uniform(a[0] - 0.3 * w, a[-1] + 0.3 * w, 6_000_000) for a, w in zip(axes, span)]
+        g, o = make_pair(0, axes, v, LIN, WRAP, dtype=np.float64)
+        want, st_want = o.eval(cols, nthreads=O.max_threads())
+        got, st, info = gpu_eval(g, cols)
+        assert_same(got, st, want, st_want, "wrap, random order")
+        assert info == expected_info(st_want)
+        assert _lib.lib().nint_last_query_order(g._h) == 2 and _lib.lib().nint_last_incoherent_route(g._h) == route
 
 
 def test_config4_interpnd_f32_n5_wrap_fill():

@@ -474,6 +474,65 @@ def test_binned_tile_route(monkeypatch):
     assert _lib.lib().nint_last_incoherent_route(g._h) == 1
 
 
+def test_slab_list_route(monkeypatch):
+    # Incoherent batches on 3-D Linear tables far beyond L2 are split once, chunk by chunk, into lists by slab of the
+    # cell-packed table, evaluated list by list and merged back into query order (nint_part.cuh).  Forced here on small
+    # tables with a tiny slab size (many lists) and small segments, ragged last chunks included.
+    from gpu_util import assert_same, expected_info, gpu_eval, make_pair
+
+    from ninterp_b200 import _lib
+
+    monkeypatch.setenv("NINT_SLAB_MIN_BYTES", "0")
+    monkeypatch.setenv("NINT_SLAB_MIN_POINTS", "0")
+    monkeypatch.setenv("NINT_ROUTE", "part")
+    monkeypatch.setenv("NINT_PROBE_SHIFT", "0")
+    rng = np.random.default_rng(777)
+    for kind, lens, dtype, mode, slab_mb, seg_shift, n in [(FIXED, (40, 9, 8), np.float64, "uniform", 0.008, 14, 300_001),
+                                                           (FIXED, (37, 35, 70), np.float64, "nonuniform", 0.3, 17, 300_001),
+                                                           (ND, (21, 40, 36), np.float32, "nonuniform", 0.1, 28, 300_001),
+                                                           (ND, (50, 18, 34), np.float64, "uniform", 0.3, 16, 123_457),
+                                                           (FIXED, (18, 67, 72), np.float32, "uniform", 0.2, 28, 4_097),
+                                                           (FIXED, (45, 33, 66), np.float64, "analytic", 0.8, 17, 300_001),
+                                                           (FIXED, (3, 33, 66), np.float64, "uniform", 0.1, 15, 100_000)]:
+        monkeypatch.setenv("NINT_PART_SLAB_MB", str(slab_mb))
+        monkeypatch.setenv("NINT_PART_SEG_SHIFT", str(seg_shift))
+        monkeypatch.setenv("NINT_PROBE_MAX_DISTINCT", str(min(int(np.prod([l - 1 for l in lens])) // 3, 2000)))
+        axes = _axes(rng, lens, dtype, mode)
+        values = rng.uniform(-1, 1, lens).astype(dtype)
+        for extrap in (ERROR, CLAMP, ENABLE, FILL, WRAP):
+            g, o = make_pair(kind, axes, values, LIN, extrap, fill=-2.5, dtype=dtype)
+            cols = _queries(rng, axes, n, dtype, 0.05)
+            for d in range(len(lens)):  # nodes (list boundaries are nodes), their neighbours, non-finite values
+                a = np.asarray(axes[d], dtype=dtype)
+                special = np.concatenate([a, np.nextafter(a, dtype(np.inf)), np.nextafter(a, dtype(-np.inf)),
+                                          np.array([np.nan, np.inf, -np.inf], dtype=dtype)])
+                where = rng.choice(n, special.size, replace=False)
+                cols[d][where] = special
+            want, st_want = o.eval(cols, nthreads=O.max_threads())
+            got, st, info = gpu_eval(g, cols)
+            assert_same(got, st, want, st_want, f"slab lists random {lens} {extrap}")
+            assert info == expected_info(st_want)
+            assert _lib.lib().nint_last_query_order(g._h) == 2
+            assert _lib.lib().nint_last_incoherent_route(g._h) == 3
+            got, st, _ = gpu_eval(g, cols, aos=True)
+            assert_same(got, st, want, st_want, f"slab lists aos {lens} {extrap}")
+            # coherent order (sorted by cell): the probe sends it to the single pass
+            order = np.lexsort([np.searchsorted(axes[2], cols[2]), np.searchsorted(axes[1], cols[1]),
+                                np.searchsorted(axes[0], cols[0])])
+            got, st, info = gpu_eval(g, [c[order] for c in cols])
+            assert_same(got, st, want[order], st_want[order], f"slab lists sorted {lens} {extrap}")
+            if n >= 100_000:  # (fewer points than cells: consecutive queries do not share cells in any order)
+                assert _lib.lib().nint_last_query_order(g._h) == 1
+        # every query in the first cells of axis 0, probe forced to "incoherent": one list holds whole chunks
+        monkeypatch.setenv("NINT_PROBE_MAX_DISTINCT", "0")
+        g, o = make_pair(kind, axes, values, LIN, ERROR, dtype=dtype)
+        cols = [rng.uniform(a[0], a[min(1, len(a) - 1)], n).astype(dtype) for a in axes]
+        got, st, info = gpu_eval(g, cols)
+        want, st_want = o.eval(cols, nthreads=O.max_threads())
+        assert_same(got, st, want, st_want, f"slab lists, one list {lens}")
+        assert _lib.lib().nint_last_incoherent_route(g._h) == 3
+
+
 def test_concurrent_batches_on_one_handle(monkeypatch):
     # include/ninterp_cuda.h: a handle is immutable during batch calls, so several host threads may evaluate
     # batches on their own streams at once -- on the single-pass route and on the probed one (order flag ring)
@@ -489,11 +548,15 @@ def test_concurrent_batches_on_one_handle(monkeypatch):
     dev = torch.device("cuda", 0)
     monkeypatch.setenv("NINT_PROBE_SHIFT", "0")
     monkeypatch.setenv("NINT_PROBE_MAX_DISTINCT", "600")
-    for passes in ("0", "3", "tile"):
+    for passes in ("0", "3", "tile", "part"):
         if passes == "tile":  # binned route: every call draws its lists from the handle's pool in stream order
             monkeypatch.delenv("NINT_SLABS")
             monkeypatch.setenv("NINT_ROUTE", "tile")
             monkeypatch.setenv("NINT_TILE_SC_SHIFT", "16")
+        elif passes == "part":  # slab lists: the same, and every call has its own work counter
+            monkeypatch.setenv("NINT_ROUTE", "part")
+            monkeypatch.setenv("NINT_PART_SLAB_MB", "0.008")
+            monkeypatch.setenv("NINT_PART_SEG_SHIFT", "16")
         else:
             monkeypatch.setenv("NINT_SLABS", passes)
         axes = _axes(rng, (40, 9, 8), np.float64, "uniform")

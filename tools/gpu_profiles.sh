@@ -14,7 +14,8 @@ cap() {  # name, kernel regex, count, command...
   ncu -i /tmp/r2p_$name.ncu-rep --page source --csv > /tmp/r2p_src_$name.csv 2>/dev/null && python tools/ncu_source.py /tmp/r2p_src_$name.csv | awk '!seen[$0]++' > gpurun_out/r2p_source_$name.txt 2>&1
   rm -f /tmp/r2p_$name.ncu-rep /tmp/r2p_src_$name.csv
 }
-cap slab "slab_kernel" 3 $P --case random --points 1e9 --launches 1
+cap lists "part_" 3 $P --case random --points 2.6e8 --launches 1
+cap slab "slab_kernel" 3 env NINT_ROUTE=slab $P --case random --points 1e9 --launches 1
 cap sorted "interp_kernel" 1 $P --case sorted --points 1e9 --launches 1
 cap tilesorted "interp_kernel" 1 $P --case tilesorted --points 1e9 --launches 1
 cap tiles "tile_" 2 env NINT_ROUTE=tile $P --case random --points 2.6e8 --launches 1
