@@ -83,25 +83,31 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_scatter_kernel(const __g
     __shared__ T s_thr[kPartMaxLists];
     if (P.mode_flag != nullptr && *P.mode_flag != P.mode_want) return;
     const unsigned t = threadIdx.x, lane = t & 31u, lt = (1u << lane) - 1u;
-    const unsigned c = blockIdx.x;
-    const unsigned base = c << kPartChunkShift;
     const unsigned n = (unsigned)P.n;
-    if (t < (unsigned)kPartMaxLists) {
-        s_cnt[t] = 0u;
-        s_thr[t] = G.thr[t];
-    }
-    if (c == 0 && t == 0) *G.ticket = 0u;
+    if (t < (unsigned)kPartMaxLists) s_thr[t] = G.thr[t];
+    if (blockIdx.x == 0 && t == 0) *G.ticket = 0u;
+    // resident CTAs walk the chunks (a CTA per chunk would be 65536 CTAs per segment, which cost a coherent batch --
+    // where this launch only reads the verdict and returns -- 25 us each time)
+    // the first two columns of a chunk are requested while the previous chunk drains (its bulk stores read the staged
+    // records, then a barrier): one of the two DRAM round trips of a chunk is off the critical path
     T x[kPartPer], y[kPartPer];
+    auto request_xy = [&](unsigned c) {
+        const unsigned base = c << kPartChunkShift;
 #pragma unroll
-    for (int r = 0; r < kPartPer; ++r) {
-        const unsigned i = base + r * kPartThreads + t;
-        x[r] = (i < n) ? ld_stream(P.coords[0] + (size_t)i * P.coord_stride) : quiet_nan<T>();
-    }
+        for (int r = 0; r < kPartPer; ++r) {
+            const unsigned i = base + r * kPartThreads + t;
+            x[r] = (c < G.nchunks && i < n) ? ld_stream(P.coords[0] + (size_t)i * P.coord_stride) : quiet_nan<T>();
+        }
 #pragma unroll
-    for (int r = 0; r < kPartPer; ++r) {
-        const unsigned i = base + r * kPartThreads + t;
-        y[r] = (i < n) ? ld_stream(P.coords[1] + (size_t)i * P.coord_stride) : T(0);
-    }
+        for (int r = 0; r < kPartPer; ++r) {
+            const unsigned i = base + r * kPartThreads + t;
+            y[r] = (c < G.nchunks && i < n) ? ld_stream(P.coords[1] + (size_t)i * P.coord_stride) : T(0);
+        }
+    };
+    request_xy(blockIdx.x);
+    for (unsigned c = blockIdx.x; c < G.nchunks; c += gridDim.x) {
+    const unsigned base = c << kPartChunkShift;
+    if (t < (unsigned)kPartMaxLists) s_cnt[t] = 0u;
     __syncthreads();
     // place inside the list: one shared-memory atomic per group of lanes with the same list
     unsigned pk[kPartPer];  // place inside the list | list << 16, then the place inside the chunk
@@ -141,15 +147,18 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_scatter_kernel(const __g
             G.pos[i] = (unsigned short)pk[r];
         }
     }
+    {
+        T z[kPartPer];
 #pragma unroll
-    for (int r = 0; r < kPartPer; ++r) {
-        const unsigned i = base + r * kPartThreads + t;
-        x[r] = (i < n) ? ld_stream(P.coords[2] + (size_t)i * P.coord_stride) : T(0);
-    }
+        for (int r = 0; r < kPartPer; ++r) {
+            const unsigned i = base + r * kPartThreads + t;
+            z[r] = (i < n) ? ld_stream(P.coords[2] + (size_t)i * P.coord_stride) : T(0);
+        }
 #pragma unroll
-    for (int r = 0; r < kPartPer; ++r) {
-        const unsigned i = base + r * kPartThreads + t;
-        if (i < n) s_rec[2 * kPartChunk + pk[r]] = x[r];
+        for (int r = 0; r < kPartPer; ++r) {
+            const unsigned i = base + r * kPartThreads + t;
+            if (i < n) s_rec[2 * kPartChunk + pk[r]] = z[r];
+        }
     }
     // whole chunks leave (the lists are allocated in whole chunks; what lies beyond a ragged chunk's points is never read)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -158,7 +167,10 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_scatter_kernel(const __g
 #pragma unroll
         for (int d = 0; d < 3; ++d) bulk_store(G.rec[d] + base, s_rec + d * kPartChunk, kPartChunk * (unsigned)sizeof(T));
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    request_xy(c + gridDim.x);
+    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();  // the staged chunk has been read: the next one may be written
     }
 }
 
@@ -193,8 +205,9 @@ __device__ __forceinline__ T part_point(const Params<T>& P, const unsigned char*
     return result;
 }
 
+// f64: 80 registers, 3 CTAs; f32: 64 registers, 4 CTAs (measured: 17.4 -> 16.3 ms; f64 at 64 registers spills: 29.5 ms)
 #ifndef NINT_PART_CTAS
-#define NINT_PART_CTAS 3
+#define NINT_PART_CTAS (sizeof(T) == 4 ? 4 : 3)
 #endif
 #ifndef NINT_PART_AHEAD
 #define NINT_PART_AHEAD 2
@@ -310,52 +323,70 @@ __global__ void __launch_bounds__(kBlock, NINT_PART_CTAS) part_eval_kernel(const
     }
 }
 
+// Shared memory of part_merge_kernel: two buffers of a chunk's results and status bytes
+template <class T>
+constexpr unsigned part_merge_smem() { return 2u * kPartChunk * ((unsigned)sizeof(T) + 1u); }
+
 template <class T>
 __global__ void __launch_bounds__(kPartThreads, 3) part_merge_kernel(const __grid_constant__ Params<T> P,
                                                                      const __grid_constant__ PartGeom<T> G) {
     extern __shared__ __align__(128) unsigned char part_smem[];
-    T* s_vals = reinterpret_cast<T*>(part_smem);                             // [kPartChunk]
-    uint8_t* s_stat = part_smem + (size_t)kPartChunk * sizeof(T);            // [kPartChunk]
-    __shared__ unsigned long long bar;
+    constexpr unsigned kBuf = kPartChunk * ((unsigned)sizeof(T) + 1u);  // results, then status bytes
+    __shared__ unsigned long long bar[2];
     __shared__ unsigned long long s_info[4];  // n_error, n_panic, first_error, first_panic
     if (P.mode_flag != nullptr && *P.mode_flag != P.mode_want) return;
     const unsigned t = threadIdx.x;
-    const unsigned base = blockIdx.x << kPartChunkShift;
     const unsigned n = (unsigned)P.n;
     if (t < 4) s_info[t] = (t < 2) ? 0ull : ~0ull;
     if (t == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (t == 0) {
-        const unsigned long long pol = l2_policy_evict_first();
-        mbar_expect_tx(&bar, kPartChunk * (unsigned)sizeof(T) + kPartChunk);
-        bulk_load(s_vals, G.vals + base, kPartChunk * (unsigned)sizeof(T), &bar, pol);
-        bulk_load(s_stat, G.stat + base, kPartChunk, &bar, pol);
-    }
-    unsigned short ps[kPartPer];
+    // resident CTAs walk the chunks; the next chunk's results are on their way into the other buffer meanwhile
+    auto request = [&](unsigned c, unsigned b) {
+        if (t == 0 && c < G.nchunks) {
+            const unsigned long long pol = l2_policy_evict_first();
+            const unsigned base = c << kPartChunkShift;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // an earlier chunk was read from this buffer
+            mbar_expect_tx(&bar[b], kBuf);
+            bulk_load(part_smem + b * kBuf, G.vals + base, kPartChunk * (unsigned)sizeof(T), &bar[b], pol);
+            bulk_load(part_smem + b * kBuf + kPartChunk * sizeof(T), G.stat + base, kPartChunk, &bar[b], pol);
+        }
+    };
+    request(blockIdx.x, 0u);
+    unsigned it = 0u;
+    for (unsigned c = blockIdx.x; c < G.nchunks; c += gridDim.x, ++it) {
+        const unsigned b = it & 1u;
+        const unsigned base = c << kPartChunkShift;
+        request(c + gridDim.x, b ^ 1u);  // (that buffer's last readers passed the barrier at the end of the previous turn)
+        unsigned short ps[kPartPer];
 #pragma unroll
-    for (int r = 0; r < kPartPer; ++r) {
-        const unsigned i = base + r * kPartThreads + t;
-        ps[r] = (i < n) ? __ldcs(G.pos + i) : (unsigned short)0;
-    }
-    mbar_wait(&bar, 0);
+        for (int r = 0; r < kPartPer; ++r) {
+            const unsigned i = base + r * kPartThreads + t;
+            ps[r] = (i < n) ? __ldcs(G.pos + i) : (unsigned short)0;
+        }
+        const T* s_vals = reinterpret_cast<const T*>(part_smem + b * kBuf);
+        const uint8_t* s_stat = part_smem + b * kBuf + kPartChunk * sizeof(T);
+        mbar_wait(&bar[b], (it >> 1) & 1u);
 #pragma unroll
-    for (int r = 0; r < kPartPer; ++r) {
-        const unsigned i = base + r * kPartThreads + t;
-        if (i < n) {
-            NINT_ASSERT(ps[r] < kPartChunk);
-            const T v = s_vals[ps[r]];
-            const unsigned status = s_stat[ps[r]];
-            st_stream(P.out + i, v);
-            if (P.status) P.status[i] = (uint8_t)status;
-            if (status != NINT_STATUS_OK) {
-                const int slot = (status == NINT_STATUS_PANIC) ? 1 : 0;
-                atomicAdd(&s_info[slot], 1ull);
-                atomicMin(&s_info[2 + slot], (unsigned long long)i + P.index_base);
+        for (int r = 0; r < kPartPer; ++r) {
+            const unsigned i = base + r * kPartThreads + t;
+            if (i < n) {
+                NINT_ASSERT(ps[r] < kPartChunk);
+                const T v = s_vals[ps[r]];
+                const unsigned status = s_stat[ps[r]];
+                st_stream(P.out + i, v);
+                if (P.status) P.status[i] = (uint8_t)status;
+                if (status != NINT_STATUS_OK) {
+                    const int slot = (status == NINT_STATUS_PANIC) ? 1 : 0;
+                    atomicAdd(&s_info[slot], 1ull);
+                    atomicMin(&s_info[2 + slot], (unsigned long long)i + P.index_base);
+                }
             }
         }
+        __syncthreads();  // every thread has its values: this buffer may be refilled
     }
     if (P.info) {
         __syncthreads();

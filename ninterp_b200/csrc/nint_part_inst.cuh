@@ -64,7 +64,8 @@ cudaError_t launch_part<NINT_T>(const Params<NINT_T>& P, const PartGeom<NINT_T>&
         // per device and function: set on every launch (a host thread may drive several GPUs)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<G.nchunks, kPartThreads, smem, stream>>>(P, G);
+        const unsigned cap = (unsigned)cfg.sm_count * 2u;  // __launch_bounds__(kPartThreads, 2), 96/48 KB of shared memory each
+        kern<<<G.nchunks < cap ? G.nchunks : cap, kPartThreads, smem, stream>>>(P, G);
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -73,8 +74,11 @@ cudaError_t launch_part<NINT_T>(const Params<NINT_T>& P, const PartGeom<NINT_T>&
     if (e != cudaSuccess) return e;
     {
         auto kern = part_merge_kernel<T>;
-        const unsigned smem = kPartChunk * ((unsigned)sizeof(T) + 1u);
-        kern<<<G.nchunks, kPartThreads, smem, stream>>>(P, G);
+        const unsigned smem = part_merge_smem<T>();
+        cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ea != cudaSuccess) return ea;
+        const unsigned cap = (unsigned)cfg.sm_count * 3u;  // __launch_bounds__(kPartThreads, 3)
+        kern<<<G.nchunks < cap ? G.nchunks : cap, kPartThreads, smem, stream>>>(P, G);
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
         e = cudaGetLastError();
     }
