@@ -974,6 +974,8 @@ int launch_parts(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
         if (!(h->ax[d].flags & nint::kAxisAnalytic)) pl.all_analytic = 0;
     pl.sm_count = cfg.sm_count;
     pl.smem_bytes = cfg.smem_bytes;
+    pl.grid_div = std::getenv("NINT_PART_GRID_DIV") ? std::atoi(std::getenv("NINT_PART_GRID_DIV")) : 0;
+    pl.merge_div = std::getenv("NINT_PART_MERGE_DIV") ? std::atoi(std::getenv("NINT_PART_MERGE_DIV")) : 4;  // measured: 25.9 -> 25.6 ms
     pl.stream = stream;
     const T* cols0[3] = {P.coords[0], P.coords[1], P.coords[2]};
     T* out0 = P.out;

@@ -285,6 +285,10 @@ __global__ void __launch_bounds__(kBlock, NINT_PART_CTAS) part_eval_kernel(const
 #pragma unroll
         for (int d = 0; d < 3; ++d) q.v[d] = ld_stream(G.rec[d] + idx);
     };
+    // The f64 kernel sits at the edge of its 80 registers and is sensitive to the shape of this loop.  Measured on the
+    // headline batch (25.8 ms in this form): an `inflight` counter and idx == ~0u for idle lanes instead of the flags
+    // 32.2 ms; the runs of a ticket walked as one sequence so that only a ticket's last group is ragged (instead of one
+    // group in ten) 32.3 ms; the slots taking turns in an unrolled trip of three groups (no register moves) 31.7 ms.
     // kAhead groups of records are in flight beyond the one being evaluated (a record load is a DRAM round trip, and a
     // group's evaluation -- two dependent L2 gathers -- is shorter than that under load)
     constexpr int kAhead = NINT_PART_AHEAD;
@@ -409,6 +413,7 @@ struct PartLaunch {
     int all_analytic;  // every axis is uniform with nodes exactly g0 + k * h: the evaluate kernel computes them
     int sm_count;
     unsigned smem_bytes;  // axis pack
+    int grid_div, merge_div;  // tuning: > 0 = one CTA per that many chunks in the scatter / merge kernel instead of resident CTAs
     void* stream;
 };
 
