@@ -966,6 +966,16 @@ int launch_parts(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
     q += up((size_t)lists * max_chunks * sizeof(unsigned));
     G.ticket = (unsigned*)q;
     G.run_stride = max_chunks;
+    // slab prefetch (NINT_PART_PREFETCH_KB: piece size, 0 = off)
+    long pf_kb = 0;
+    {
+        const unsigned long long plane = (unsigned long long)(h->ncells / (unsigned long long)cells0) * 8ull * sizeof(T);  // packed bytes per axis-0 cell
+        G.slab_bytes = plane * (unsigned long long)per;
+        G.table_bytes = (unsigned long long)h->ncells * 8ull * sizeof(T);
+        const char* e_pf = std::getenv("NINT_PART_PREFETCH_KB");
+        pf_kb = e_pf ? std::atol(e_pf) : 0;  // < 0: sized per segment so that the first ~2048 tickets of a list cover the slab
+        G.pf_piece = pf_kb > 0 ? (unsigned)std::min(pf_kb, 1024l) * 1024u : 0u;
+    }
     nint::PartLaunch pl;
     pl.is_nd = cfg.is_nd;
     pl.all_uniform = cfg.all_uniform;
@@ -990,6 +1000,11 @@ int launch_parts(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
         P.n = m;
         P.index_base = base0 + start;
         G.nchunks = (unsigned)((m + nint::kPartChunk - 1) / nint::kPartChunk);
+        if (pf_kb < 0) {
+            const unsigned long long tickets = std::min<unsigned long long>((G.nchunks + nint::kPartTicket - 1) / nint::kPartTicket, 2048ull);
+            const unsigned long long piece = ((G.slab_bytes + tickets - 1) / tickets + 4095ull) & ~4095ull;
+            G.pf_piece = (unsigned)std::min<unsigned long long>(piece, 1ull << 20);
+        }
         const cudaError_t e = nint::launch_part<T>(P, G, pl);
         if (e != cudaSuccess) rc = cuda_fail(e, "slab-list route launch");
     }

@@ -27,9 +27,28 @@
 
 namespace nint {
 
-constexpr unsigned kPartChunkShift = 12;
+// Tuning knobs (defaults = the measured best, see the notes at the kernels)
+#ifndef NINT_PART_CHUNK_SHIFT
+#define NINT_PART_CHUNK_SHIFT 12
+#endif
+#ifndef NINT_PART_THREADS
+#define NINT_PART_THREADS 512
+#endif
+#ifndef NINT_PART_SCATTER_CTAS
+#define NINT_PART_SCATTER_CTAS 2
+#endif
+#ifndef NINT_PART_MERGE_CTAS
+#define NINT_PART_MERGE_CTAS 3
+#endif
+#ifndef NINT_PART_PREFETCH_Z
+#define NINT_PART_PREFETCH_Z 0  // 1: the third column is requested with the first two (needs 3 * kPartPer coordinates in registers)
+#endif
+constexpr unsigned kPartChunkShift = NINT_PART_CHUNK_SHIFT;
 constexpr unsigned kPartChunk = 1u << kPartChunkShift;  // points per chunk: positions and run bounds fit 16 bits
-constexpr int kPartThreads = 512;
+static_assert(kPartChunkShift >= 10 && kPartChunkShift <= 15, "positions and run bounds are 16-bit");
+constexpr int kPartThreads = NINT_PART_THREADS;
+constexpr int kPartScatterCtas = NINT_PART_SCATTER_CTAS;
+constexpr int kPartMergeCtas = NINT_PART_MERGE_CTAS;
 constexpr int kPartPer = (int)kPartChunk / kPartThreads;  // points per thread in the scatter and merge kernels
 constexpr int kPartMaxLists = 32;
 
@@ -49,8 +68,16 @@ struct PartGeom {
     unsigned* ticket;      // work counter of the evaluate kernel (zeroed by the scatter kernel)
     unsigned run_stride;
     unsigned nchunks;
+    // slab prefetch of the evaluate kernel: list k gathers from bytes [k * slab_bytes, (k + 1) * slab_bytes) of the
+    // packed table (table_bytes in all); the warp that draws ticket i of a list asks for piece i of its slab
+    unsigned long long slab_bytes, table_bytes;
+    unsigned pf_piece;  // bytes per piece (multiple of 16); 0 = no prefetch
 };
 
+// Asks the TMA engine to bring `bytes` (multiple of 16) at `src` into L2; nothing waits for it.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes, unsigned long long pol) {
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void bulk_store(void* dst, const void* src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
 }
@@ -74,7 +101,7 @@ __device__ __forceinline__ int part_list(const PartGeom<T>& G, const T* s_thr, T
 // the slots they were read from and permuted in place after a barrier -- no coordinate registers, every request out
 // before the first wait -- ran the kernel at 3.02 ms per 2^28 points against 2.73 ms for this form.
 template <class T>
-__global__ void __launch_bounds__(kPartThreads, 2) part_scatter_kernel(const __grid_constant__ Params<T> P,
+__global__ void __launch_bounds__(kPartThreads, kPartScatterCtas) part_scatter_kernel(const __grid_constant__ Params<T> P,
                                                                        const __grid_constant__ PartGeom<T> G) {
     extern __shared__ __align__(128) unsigned char part_smem[];
     T* s_rec = reinterpret_cast<T*>(part_smem);  // [3][kPartChunk]
@@ -91,6 +118,9 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_scatter_kernel(const __g
     // the first two columns of a chunk are requested while the previous chunk drains (its bulk stores read the staged
     // records, then a barrier): one of the two DRAM round trips of a chunk is off the critical path
     T x[kPartPer], y[kPartPer];
+#if NINT_PART_PREFETCH_Z
+    T z[kPartPer];
+#endif
     auto request_xy = [&](unsigned c) {
         const unsigned base = c << kPartChunkShift;
 #pragma unroll
@@ -103,6 +133,13 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_scatter_kernel(const __g
             const unsigned i = base + r * kPartThreads + t;
             y[r] = (c < G.nchunks && i < n) ? ld_stream(P.coords[1] + (size_t)i * P.coord_stride) : T(0);
         }
+#if NINT_PART_PREFETCH_Z
+#pragma unroll
+        for (int r = 0; r < kPartPer; ++r) {
+            const unsigned i = base + r * kPartThreads + t;
+            z[r] = (c < G.nchunks && i < n) ? ld_stream(P.coords[2] + (size_t)i * P.coord_stride) : T(0);
+        }
+#endif
     };
     request_xy(blockIdx.x);
     for (unsigned c = blockIdx.x; c < G.nchunks; c += gridDim.x) {
@@ -148,12 +185,14 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_scatter_kernel(const __g
         }
     }
     {
+#if !NINT_PART_PREFETCH_Z
         T z[kPartPer];
 #pragma unroll
         for (int r = 0; r < kPartPer; ++r) {
             const unsigned i = base + r * kPartThreads + t;
             z[r] = (i < n) ? ld_stream(P.coords[2] + (size_t)i * P.coord_stride) : T(0);
         }
+#endif
 #pragma unroll
         for (int r = 0; r < kPartPer; ++r) {
             const unsigned i = base + r * kPartThreads + t;
@@ -205,12 +244,82 @@ __device__ __forceinline__ T part_point(const Params<T>& P, const unsigned char*
     return result;
 }
 
+// part_point in phases, for the kernel form that evaluates several groups per trip: the weights of every group (these
+// contain branches: the division's slow path, the retry of a non-uniform axis), then all gathers, then the blends.
+// The operations on a point's data are those of fast_point (nint_device.cuh), in the same order.
+template <class T, bool IS_ND, bool UNI, bool FIRST>
+__device__ __forceinline__ bool part_weights_table(const Params<T>& P, const unsigned char* pack, const T (&p)[3], int (&k)[3], T (&t)[3]) {
+    constexpr bool kCollapse = IS_ND;
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const unsigned* guess = UNI ? nullptr : reinterpret_cast<const unsigned*>(pack + P.guess_off[d]);
+        ok = guess_cell<T, UNI>(load_axis<T>(P, pack, d), guess, p[d], k[d]) && ok;
+    }
+    if (!ok) return false;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        T a, w, r;
+        ok = verify_cell_linear<T, kCollapse, FIRST>(load_axis<T>(P, pack, d), p[d], k[d], a, w, r) && ok;
+        t[d] = div_markstein<T>(a, w, r);
+    }
+    if (!UNI && !ok) {
+        ok = true;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            T a, w, r;
+            ok = verify_linear_retry<T, kCollapse, FIRST, UNI>(load_axis<T>(P, pack, d), p[d], k[d], a, w, r) && ok;
+            t[d] = div_markstein<T>(a, w, r);
+        }
+    }
+    return ok;
+}
+// false: the point takes the general path (its gather is still issued, from cell 0)
+template <class T, bool IS_ND, int PRE, bool UNI, bool ANA>
+__device__ __forceinline__ bool part_weights(const Params<T>& P, const unsigned char* pack, const Point<T, 3>& q, unsigned& cell, T (&t)[3]) {
+    T p[3];
+    bool oob = false;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        p[d] = (PRE == kPreClamp) ? clamp_coord(q.v[d], P.g0[d], P.gl[d]) : q.v[d];
+        if (PRE == kPreWrap) oob = oob || !(P.g0[d] <= q.v[d] && q.v[d] <= P.gl[d]);
+    }
+    if (PRE == kPreWrap) {
+        if (oob) {
+            const Point<T, 3> w = wrap_point<T, 3>(P, q);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) p[d] = w.v[d];
+        }
+    }
+    int k[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) t[d] = T(0);
+    bool ok;
+    if constexpr (ANA) ok = fast_weights_analytic<T, 3, IS_ND, PRE == kPreClamp>(P, p, k, t);
+    else ok = part_weights_table<T, IS_ND, UNI, PRE == kPreClamp>(P, pack, p, k, t);
+    cell = 0u;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) cell += (unsigned)k[d] * (unsigned)P.cstride[d];
+    if (!ok) cell = 0u;
+    NINT_ASSERT((unsigned long long)cell < P.ncells);
+    return ok;
+}
+template <class T, int N, bool IS_ND>
+__device__ __forceinline__ T part_general(const Params<T>& P, const unsigned char* pack, const Point<T, N>& q, unsigned& status) {
+    const Outcome<T> o = general_point<T, N, IS_ND, NINT_LINEAR>(P, pack, q);
+    status = o.status;
+    return (status != NINT_STATUS_OK) ? quiet_nan<T>() : o.value;
+}
+
 // f64: 80 registers, 3 CTAs; f32: 64 registers, 4 CTAs (measured: 17.4 -> 16.3 ms; f64 at 64 registers spills: 29.5 ms)
 #ifndef NINT_PART_CTAS
 #define NINT_PART_CTAS (sizeof(T) == 4 ? 4 : 3)
 #endif
 #ifndef NINT_PART_AHEAD
 #define NINT_PART_AHEAD 2
+#endif
+#ifndef NINT_PART_ILP
+#define NINT_PART_ILP 1
 #endif
 
 constexpr unsigned kPartTicket = 4;  // chunks per ticket of the evaluate kernel
@@ -247,6 +356,22 @@ __global__ void __launch_bounds__(kBlock, NINT_PART_CTAS) part_eval_kernel(const
         const unsigned c = (t - k * tpl) * kPartTicket + lane;
         return (lane < kPartTicket && c < G.nchunks) ? __ldg(G.runs + (size_t)k * G.run_stride + c) : 0u;
     };
+    // The first gathers of a list find nothing of its slab in L2: one lane in thirteen then waits for DRAM, which is
+    // nearly every group of 32.  The warps entering a list (they all do at about the same time) ask for the slab
+    // piece by piece instead -- sequential reads, ~10 us for 40 MB -- so the groups behind them hit.
+    auto prefetch_piece = [&](unsigned t) {
+        const unsigned k = t / tpl;
+        const unsigned long long off = (unsigned long long)(t - k * tpl) * G.pf_piece;
+        if (off < G.slab_bytes) {
+            const unsigned long long at = (unsigned long long)k * G.slab_bytes + off;
+            if (at < G.table_bytes) {
+                unsigned long long len = G.slab_bytes - off;
+                if (len > G.pf_piece) len = G.pf_piece;
+                if (len > G.table_bytes - at) len = G.table_bytes - at;
+                bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(P.cells) + at, (unsigned)len & ~15u, pol);
+            }
+        }
+    };
     unsigned raw = draw();
     unsigned t_next = __shfl_sync(0xffffffffu, raw, 0);
     unsigned ent_next = entries(t_next);
@@ -270,6 +395,7 @@ __global__ void __launch_bounds__(kBlock, NINT_PART_CTAS) part_eval_kernel(const
                 if (t_next >= total) return false;
                 ent = ent_next;
                 cb = (t_next % tpl) * kPartTicket;
+                if (G.pf_piece != 0u && lane == 0u) prefetch_piece(t_next);
                 j = 0u;
                 raw = draw();
                 pending = true;
@@ -292,9 +418,11 @@ __global__ void __launch_bounds__(kBlock, NINT_PART_CTAS) part_eval_kernel(const
     // kAhead groups of records are in flight beyond the one being evaluated (a record load is a DRAM round trip, and a
     // group's evaluation -- two dependent L2 gathers -- is shorter than that under load)
     constexpr int kAhead = NINT_PART_AHEAD;
-    Point<T, 3> q[kAhead + 1];
-    unsigned idx[kAhead + 1];
-    bool live[kAhead + 1], has[kAhead + 1];
+    constexpr int kIlp = NINT_PART_ILP;  // groups evaluated together: their gathers are in flight at the same time
+    constexpr int kSlots = kAhead + kIlp;
+    Point<T, 3> q[kSlots];
+    unsigned idx[kSlots];
+    bool live[kSlots], has[kSlots];
     bool done = false;
     auto load_slot = [&](int s) {
         has[s] = !done && advance();
@@ -309,20 +437,73 @@ __global__ void __launch_bounds__(kBlock, NINT_PART_CTAS) part_eval_kernel(const
     };
 #pragma unroll
     for (int s = 0; s < kAhead; ++s) load_slot(s);
-    while (has[0]) {
-        load_slot(kAhead);
-        if (live[0]) {
-            unsigned status;
-            const T res = part_point<T, 3, IS_ND, PRE, UNI, ANA>(P, pack, pol, q[0], status);
-            st_stream(G.vals + idx[0], res);
-            G.stat[idx[0]] = (uint8_t)status;
-        }
+    if constexpr (kIlp == 1) {
+        while (has[0]) {
+            load_slot(kAhead);
+            if (live[0]) {
+                unsigned status;
+                const T res = part_point<T, 3, IS_ND, PRE, UNI, ANA>(P, pack, pol, q[0], status);
+                st_stream(G.vals + idx[0], res);
+                G.stat[idx[0]] = (uint8_t)status;
+            }
 #pragma unroll
-        for (int s = 0; s < kAhead; ++s) {
-            q[s] = q[s + 1];
-            idx[s] = idx[s + 1];
-            live[s] = live[s + 1];
-            has[s] = has[s + 1];
+            for (int s = 0; s < kAhead; ++s) {
+                q[s] = q[s + 1];
+                idx[s] = idx[s + 1];
+                live[s] = live[s + 1];
+                has[s] = has[s + 1];
+            }
+        }
+    } else {
+        // kIlp groups per trip: every fast path first (branch-free up to its verdict, so the gathers of all of them are
+        // issued before the first blend waits), then the general path for whatever declined
+        while (has[0]) {
+#pragma unroll
+            for (int s = 0; s < kIlp; ++s) load_slot(kAhead + s);
+            T res[kIlp];
+            bool ok[kIlp];
+            unsigned cell[kIlp];
+            T t[kIlp][3];
+            T cube[kIlp][8];
+#pragma unroll
+            for (int s = 0; s < kIlp; ++s) {  // idle lanes evaluate the grid's first node
+                if (!live[s]) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) q[s].v[d] = P.g0[d];
+                }
+                ok[s] = part_weights<T, IS_ND, PRE, UNI, ANA>(P, pack, q[s], cell[s], t[s]);
+            }
+#pragma unroll
+            for (int s = 0; s < kIlp; ++s) ld_cells_keep<8>(P.cells + (size_t)cell[s] * 8, pol, cube[s]);
+#pragma unroll
+            for (int s = 0; s < kIlp; ++s) {
+                // reduce axis 0 first, then 1, 2: v_l * (1 - t) + v_u * t, each operation rounded separately (fast_point)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const int half = 1 << (2 - d);
+                    const T td = t[s][d];
+                    const T sd = T(1) - td;
+#pragma unroll
+                    for (int j = 0; j < half; ++j) cube[s][j] = cube[s][j] * sd + cube[s][half + j] * td;
+                }
+                res[s] = cube[s][0];
+            }
+#pragma unroll
+            for (int s = 0; s < kIlp; ++s) {
+                if (live[s]) {
+                    unsigned status = NINT_STATUS_OK;
+                    if (!ok[s]) res[s] = part_general<T, 3, IS_ND>(P, pack, q[s], status);
+                    st_stream(G.vals + idx[s], res[s]);
+                    G.stat[idx[s]] = (uint8_t)status;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < kAhead; ++s) {
+                q[s] = q[s + kIlp];
+                idx[s] = idx[s + kIlp];
+                live[s] = live[s + kIlp];
+                has[s] = has[s + kIlp];
+            }
         }
     }
 }
@@ -332,7 +513,7 @@ template <class T>
 constexpr unsigned part_merge_smem() { return 2u * kPartChunk * ((unsigned)sizeof(T) + 1u); }
 
 template <class T>
-__global__ void __launch_bounds__(kPartThreads, 3) part_merge_kernel(const __grid_constant__ Params<T> P,
+__global__ void __launch_bounds__(kPartThreads, kPartMergeCtas) part_merge_kernel(const __grid_constant__ Params<T> P,
                                                                      const __grid_constant__ PartGeom<T> G) {
     extern __shared__ __align__(128) unsigned char part_smem[];
     constexpr unsigned kBuf = kPartChunk * ((unsigned)sizeof(T) + 1u);  // results, then status bytes

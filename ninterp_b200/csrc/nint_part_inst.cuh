@@ -65,7 +65,7 @@ cudaError_t launch_part<NINT_T>(const Params<NINT_T>& P, const PartGeom<NINT_T>&
         // per device and function: set on every launch (a host thread may drive several GPUs)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        unsigned cap = (unsigned)cfg.sm_count * 2u;  // __launch_bounds__(kPartThreads, 2), 96/48 KB of shared memory each
+        unsigned cap = (unsigned)cfg.sm_count * (unsigned)kPartScatterCtas;  // __launch_bounds__(kPartThreads, 2), 96/48 KB of shared memory each
         if (cfg.grid_div > 0) cap = std::max(cap, (G.nchunks + (unsigned)cfg.grid_div - 1) / (unsigned)cfg.grid_div);
         kern<<<G.nchunks < cap ? G.nchunks : cap, kPartThreads, smem, stream>>>(P, G);
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
@@ -79,7 +79,7 @@ cudaError_t launch_part<NINT_T>(const Params<NINT_T>& P, const PartGeom<NINT_T>&
         const unsigned smem = part_merge_smem<T>();
         cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ea != cudaSuccess) return ea;
-        unsigned cap = (unsigned)cfg.sm_count * 3u;  // __launch_bounds__(kPartThreads, 3)
+        unsigned cap = (unsigned)cfg.sm_count * (unsigned)kPartMergeCtas;  // __launch_bounds__(kPartThreads, 3)
         if (cfg.merge_div > 0) cap = std::max(cap, (G.nchunks + (unsigned)cfg.merge_div - 1) / (unsigned)cfg.merge_div);
         kern<<<G.nchunks < cap ? G.nchunks : cap, kPartThreads, smem, stream>>>(P, G);
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
