@@ -169,11 +169,13 @@ NINT_API int nint_interpolate(nint_handle* h, const void* point, size_t point_le
 
 /* Diagnostics: how the most recent batch on this handle was classified by the on-device order probe that runs
  * for Linear on tables well beyond L2: 0 = no probe ran, 1 = coherent (single pass on the
- * cell-packed table), 2 = incoherent (binned tiles or slab passes, see nint_last_incoherent_route).  Synchronises the device. */
+ * cell-packed table), 2 = incoherent (slab lists, slab passes or binned tiles, see nint_last_incoherent_route).
+ * Synchronises the device. */
 NINT_API int nint_last_query_order(nint_handle* h);
 
 /* Diagnostics: what the most recent batch on this handle enqueued for an incoherent verdict of the order probe:
- * 0 = nothing (no probe ran), 1 = slab passes on the plain table, 2 = binned tiles staged in shared memory by TMA.
+ * 0 = nothing (no probe ran), 1 = slab passes on the plain table, 2 = binned tiles staged in shared memory by TMA,
+ * 3 = slab lists (the batch split once by slab of the cell-packed table, evaluated list by list, merged back).
  * Host-side state, no synchronisation. */
 NINT_API int nint_last_incoherent_route(nint_handle* h);
 

@@ -893,35 +893,45 @@ int launch_tiles(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
 // ------------------------------------------------------------------------------- slab lists (nint_part.cuh)
 // Number of lists (slabs of the cell-packed table along axis 0) an incoherent batch of n points is split into; 0 = the
 // route does not apply.  Same regime as the slab passes (3-D Linear, axes staged in shared memory, a packed table the
-// single pass cannot keep in L2, a batch large enough), any Extrapolate policy.  NINT_ROUTE=part forces the route where
+// single pass cannot keep in L2, a batch large enough), any Extrapolate policy; and InterpND with four or five axes
+// under Wrap (slabs of the flattened (axis 0, axis 1) cell index, non-uniform axes included).  NINT_ROUTE=part forces the route where
 // it applies, NINT_ROUTE=slab|tile|single and NINT_SLABS exclude it; NINT_PART_SLAB_MB sets the slab size.
 int part_lists(const nint_handle* h, size_t n, int* cells_per_list) {
-    if (h->constant || h->ndim_eff != 3 || h->strategy != NINT_LINEAR || !h->smem_axes || !h->d_cells) return 0;
+    if (h->constant || h->ndim_eff < 3 || h->ndim_eff > nint::kPartMaxDim || h->strategy != NINT_LINEAR || !h->smem_axes || !h->d_cells) return 0;
+    const bool wide = h->ndim_eff >= 4;  // InterpND with four or five axes: slabs of the flattened (axis 0, axis 1) cell index
     const char* route = std::getenv("NINT_ROUTE");
     const bool forced = route && !std::strcmp(route, "part");
     if (route && !forced) return 0;
     if (std::getenv("NINT_SLABS") && !forced) return 0;
     // Measured on B200 (256^3, 1e9 random points; slab lists vs slab passes): uniform axes 25.6 vs 30.6 ms (f64, nodes
     // computed), 28.3 vs 30.6 ms (f64, nodes loaded), 17.4 vs 19.3 ms (f32); non-uniform axes 36.5 vs 35.7 ms.  So
-    // the lists take the interpolators whose axes are all uniform; the others keep the slab passes / binned tiles.
-    for (int d = 0; d < h->ndim_eff && !forced; ++d)
+    // the lists take the 3-D interpolators whose axes are all uniform; the others keep the slab passes / binned tiles.
+    for (int d = 0; d < h->ndim_eff && !forced && !wide; ++d)
         if ((h->ax[d].flags & (nint::kAxisUniform | nint::kAxisFast)) != (nint::kAxisUniform | nint::kAxisFast)) return 0;
+    // Four and five axes: Fill and Error have the in-range compaction pass, Enable and Clamp the slab passes; the lists
+    // take Wrap, which had only the single pass (NINT_PART_ND=0 keeps it)
+    if (wide && !forced) {
+        if (h->extrap != NINT_EXTRAPOLATE_WRAP) return 0;
+        const char* e_nd = std::getenv("NINT_PART_ND");
+        if (e_nd && std::atoi(e_nd) == 0) return 0;
+    }
     const char* e_bytes = std::getenv("NINT_SLAB_MIN_BYTES");
     const char* e_points = std::getenv("NINT_SLAB_MIN_POINTS");
     const long long min_bytes = e_bytes ? std::atoll(e_bytes) : 256ll << 20;
     const long long min_points = e_points ? std::atoll(e_points) : 1ll << 22;
     if ((long long)n < min_points) return 0;
-    const double packed = (double)h->ncells * 8.0 * (double)elem_size(h->dtype);
+    const double packed = (double)h->ncells * (double)(1u << h->ndim_eff) * (double)elem_size(h->dtype);
     if (packed < (double)min_bytes) return 0;
     const char* e_mb = std::getenv("NINT_PART_SLAB_MB");
     const double slab = (e_mb ? std::atof(e_mb) : 40.0) * 1024.0 * 1024.0;
-    const int cells0 = (int)h->axis_len[0] - 1;
-    const double plane = packed / (double)cells0;  // bytes of the packed table per axis-0 cell
-    int per = std::max(1, (int)std::floor(slab / plane));
-    int lists = (cells0 + per - 1) / per;
-    if (lists < 2 || lists > nint::kPartMaxLists) return 0;
-    *cells_per_list = per;
-    return lists;
+    // rows of the slab index: axis-0 cells, or (axis-0 cell, axis-1 cell) pairs
+    const long long rows = wide ? ((long long)h->axis_len[0] - 1) * ((long long)h->axis_len[1] - 1) : (long long)h->axis_len[0] - 1;
+    const double row_bytes = packed / (double)rows;  // bytes of the packed table per row
+    const long long per = std::max(1ll, (long long)std::floor(slab / row_bytes));
+    const long long lists = (rows + per - 1) / per;
+    if (lists < 2 || lists > (wide ? nint::kPartMaxListsWide : nint::kPartMaxLists)) return 0;
+    *cells_per_list = (int)per;
+    return (int)lists;
 }
 
 // Enqueues scatter + evaluate + merge for the whole launch, in segments whose lists fit the scratch budget.
@@ -937,8 +947,9 @@ int launch_parts(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
     const unsigned long long cap = (std::min(n, seg) + nint::kPartChunk - 1) / nint::kPartChunk * nint::kPartChunk;
     const unsigned max_chunks = (unsigned)(cap / nint::kPartChunk);
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const int nd = h->ndim_eff;
     const size_t col = up((size_t)cap * sizeof(T));
-    const size_t bytes = 4 * col + up((size_t)cap) + up((size_t)cap * 2) + up((size_t)lists * max_chunks * sizeof(unsigned)) + 256;
+    const size_t bytes = (size_t)(nd + 1) * col + up((size_t)cap) + up((size_t)cap * 2) + up((size_t)lists * max_chunks * sizeof(unsigned)) + 256;
     unsigned char* scratch = nullptr;
     if (cudaMallocFromPoolAsync((void**)&scratch, bytes, h->pool, stream) != cudaSuccess) {
         cudaGetLastError();
@@ -953,9 +964,11 @@ int launch_parts(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
     G.x0 = g0[0];
     G.x1 = g0[cells0];
     G.scale = (T)(h->ax[0].inv_h / (double)per);
-    for (int k = 0; k < nint::kPartMaxLists; ++k) G.thr[k] = g0[std::min(cells0, k * per)];
+    for (int k = 0; k < nint::kPartMaxLists; ++k) G.thr[k] = g0[std::min(cells0, nd == 3 ? k * per : 0)];
+    G.wide_per = (unsigned)per;
+    G.wide_cells1 = (unsigned)h->axis_len[1] - 1u;
     unsigned char* q = scratch;
-    for (int d = 0; d < 3; ++d, q += col) G.rec[d] = (T*)q;
+    for (int d = 0; d < nd; ++d, q += col) G.rec[d] = (T*)q;
     G.vals = (T*)q;
     q += col;
     G.stat = q;
@@ -966,45 +979,32 @@ int launch_parts(nint_handle* h, nint::Params<T> P, const nint::LaunchCfg& cfg, 
     q += up((size_t)lists * max_chunks * sizeof(unsigned));
     G.ticket = (unsigned*)q;
     G.run_stride = max_chunks;
-    // slab prefetch (NINT_PART_PREFETCH_KB: piece size, 0 = off)
-    long pf_kb = 0;
-    {
-        const unsigned long long plane = (unsigned long long)(h->ncells / (unsigned long long)cells0) * 8ull * sizeof(T);  // packed bytes per axis-0 cell
-        G.slab_bytes = plane * (unsigned long long)per;
-        G.table_bytes = (unsigned long long)h->ncells * 8ull * sizeof(T);
-        const char* e_pf = std::getenv("NINT_PART_PREFETCH_KB");
-        pf_kb = e_pf ? std::atol(e_pf) : 0;  // < 0: sized per segment so that the first ~2048 tickets of a list cover the slab
-        G.pf_piece = pf_kb > 0 ? (unsigned)std::min(pf_kb, 1024l) * 1024u : 0u;
-    }
     nint::PartLaunch pl;
     pl.is_nd = cfg.is_nd;
+    pl.ndim = nd;
     pl.all_uniform = cfg.all_uniform;
     pl.all_analytic = std::getenv("NINT_NO_ANALYTIC") ? 0 : 1;
-    for (int d = 0; d < 3; ++d)
+    for (int d = 0; d < nd; ++d)
         if (!(h->ax[d].flags & nint::kAxisAnalytic)) pl.all_analytic = 0;
     pl.sm_count = cfg.sm_count;
     pl.smem_bytes = cfg.smem_bytes;
     pl.grid_div = std::getenv("NINT_PART_GRID_DIV") ? std::atoi(std::getenv("NINT_PART_GRID_DIV")) : 0;
     pl.merge_div = std::getenv("NINT_PART_MERGE_DIV") ? std::atoi(std::getenv("NINT_PART_MERGE_DIV")) : 4;  // measured: 25.9 -> 25.6 ms
     pl.stream = stream;
-    const T* cols0[3] = {P.coords[0], P.coords[1], P.coords[2]};
+    const T* cols0[nint::kPartMaxDim];
+    for (int d = 0; d < nd; ++d) cols0[d] = P.coords[d];
     T* out0 = P.out;
     uint8_t* st0 = P.status;
     const unsigned long long base0 = P.index_base;
     int rc = NINT_OK;
     for (unsigned long long start = 0; start < n && rc == NINT_OK; start += seg) {
         const unsigned long long m = std::min(seg, n - start);
-        for (int d = 0; d < 3; ++d) P.coords[d] = cols0[d] + start * P.coord_stride;
+        for (int d = 0; d < nd; ++d) P.coords[d] = cols0[d] + start * P.coord_stride;
         P.out = out0 + start;
         P.status = st0 ? st0 + start : nullptr;
         P.n = m;
         P.index_base = base0 + start;
         G.nchunks = (unsigned)((m + nint::kPartChunk - 1) / nint::kPartChunk);
-        if (pf_kb < 0) {
-            const unsigned long long tickets = std::min<unsigned long long>((G.nchunks + nint::kPartTicket - 1) / nint::kPartTicket, 2048ull);
-            const unsigned long long piece = ((G.slab_bytes + tickets - 1) / tickets + 4095ull) & ~4095ull;
-            G.pf_piece = (unsigned)std::min<unsigned long long>(piece, 1ull << 20);
-        }
         const cudaError_t e = nint::launch_part<T>(P, G, pl);
         if (e != cudaSuccess) rc = cuda_fail(e, "slab-list route launch");
     }

@@ -21,46 +21,49 @@
 // measured for the slab passes, and 3.5 L1 wavefronts against 7.5.  Every point is evaluated by the same device
 // functions as everywhere else (fast_point on the packed table, general_point for the rest), so the bits are the same;
 // which list a point lands in only decides what its gathers find in L2.
+//
+// InterpND with four or five axes (kernels templated on N, WIDE scatter): the packed table is 2^N times the plain one
+// (3.7 GB for 32^5 f32) and one axis-0 plane of it is already beyond L2, so a slab is a range of the flattened
+// (axis-0 cell, axis-1 cell) index and there are up to 128 lists; the cells come from the axis records (count_less).
+//
+// What the evaluate kernel is bound by (ncu, 256^3 f64, 2.6e8 random points, 3.26 ms): the L1 data pipe.  A 64-byte
+// cell block per lane is two LDG.256 = two wavefronts per point whatever the cache level that answers; with the record
+// and result streams 2.7 wavefronts per point, 75 % of the pipe's rate (FP64 pipe 31 %, issue slots 46 %, DRAM 38 %).
+// At one wavefront per SM and clock, two per point bound ANY f64 3-D gather kernel on this part at
+// 148 SMs x 1.92 GHz / 2 = 142 Gpoints/s.  Measured and dropped on the headline batch (25.5 ms as it stands):
+//   * several groups per trip, weights of all, then all gathers, then the blends (97-128 registers, 2 CTAs):
+//     29.4-32.1 ms -- fewer warps cost more than the overlapped gathers give;
+//   * the slab of a list requested piece by piece (cp.async.bulk.prefetch.L2) by the first warps that enter the list:
+//     27.8 vs 27.8 ms without (and both slower than without the code: 8 bytes of spill at 80 registers);
+//   * four record groups in flight at 2 CTAs: 29.9 ms; slabs of 28 / 52 MB instead of 40: 30.9 / 25.7 ms;
+//     segments of 2^29 / 2^30 points instead of 2^28: 27.3 / 27.1 ms;
+//   * scatter/merge: chunks of 2048 points with 4 CTAs of 256 threads 27.0 ms, with the third column requested early
+//     26.6 ms, chunks of 4096 with the third column requested early (spills) 27.7 ms.
 #pragma once
 #include "nint_async.cuh"
 #include "nint_device.cuh"
 
 namespace nint {
 
-// Tuning knobs (defaults = the measured best, see the notes at the kernels)
-#ifndef NINT_PART_CHUNK_SHIFT
-#define NINT_PART_CHUNK_SHIFT 12
-#endif
-#ifndef NINT_PART_THREADS
-#define NINT_PART_THREADS 512
-#endif
-#ifndef NINT_PART_SCATTER_CTAS
-#define NINT_PART_SCATTER_CTAS 2
-#endif
-#ifndef NINT_PART_MERGE_CTAS
-#define NINT_PART_MERGE_CTAS 3
-#endif
-#ifndef NINT_PART_PREFETCH_Z
-#define NINT_PART_PREFETCH_Z 0  // 1: the third column is requested with the first two (needs 3 * kPartPer coordinates in registers)
-#endif
-constexpr unsigned kPartChunkShift = NINT_PART_CHUNK_SHIFT;
+constexpr unsigned kPartChunkShift = 12;
 constexpr unsigned kPartChunk = 1u << kPartChunkShift;  // points per chunk: positions and run bounds fit 16 bits
-static_assert(kPartChunkShift >= 10 && kPartChunkShift <= 15, "positions and run bounds are 16-bit");
-constexpr int kPartThreads = NINT_PART_THREADS;
-constexpr int kPartScatterCtas = NINT_PART_SCATTER_CTAS;
-constexpr int kPartMergeCtas = NINT_PART_MERGE_CTAS;
+constexpr int kPartThreads = 512;
 constexpr int kPartPer = (int)kPartChunk / kPartThreads;  // points per thread in the scatter and merge kernels
-constexpr int kPartMaxLists = 32;
+constexpr int kPartMaxLists = 32;       // narrow scatter: one slab axis, a lane of the scan warp per list
+constexpr int kPartMaxListsWide = 128;  // wide scatter (N >= 4): slabs of the flattened (axis 0, axis 1) cell index
+constexpr int kPartMaxDim = 5;
 
 template <class T>
 struct PartGeom {
-    int lists;    // K: slabs of the packed table along axis 0
+    int lists;    // K: slabs of the packed table along axis 0 (wide: along the flattened index of axes 0 and 1)
     int uniform;  // axis 0 is uniform: list = (x - x0) * scale; otherwise the thresholds are searched
     int wrap;     // Extrapolate::Wrap: out-of-range coordinates are wrapped before they are classified
     T x0, x1;     // first and last node of axis 0
     T scale;      // lists per unit length (uniform)
     T thr[kPartMaxLists];  // thr[k], k >= 1: the axis-0 node where list k starts
-    T* rec[3];             // the coordinates, every chunk rearranged into runs
+    unsigned wide_per;     // wide: flattened (axis 0, axis 1) cells per list
+    unsigned wide_cells1;  // wide: cells of axis 1
+    T* rec[kPartMaxDim];   // the coordinates, every chunk rearranged into runs
     T* vals;               // results, at the record's place
     uint8_t* stat;         // status bytes, at the record's place
     unsigned short* pos;   // place of point i inside its chunk
@@ -68,16 +71,8 @@ struct PartGeom {
     unsigned* ticket;      // work counter of the evaluate kernel (zeroed by the scatter kernel)
     unsigned run_stride;
     unsigned nchunks;
-    // slab prefetch of the evaluate kernel: list k gathers from bytes [k * slab_bytes, (k + 1) * slab_bytes) of the
-    // packed table (table_bytes in all); the warp that draws ticket i of a list asks for piece i of its slab
-    unsigned long long slab_bytes, table_bytes;
-    unsigned pf_piece;  // bytes per piece (multiple of 16); 0 = no prefetch
 };
 
-// Asks the TMA engine to bring `bytes` (multiple of 16) at `src` into L2; nothing waits for it.
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes, unsigned long long pol) {
-    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
-}
 __device__ __forceinline__ void bulk_store(void* dst, const void* src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
 }
@@ -97,11 +92,28 @@ __device__ __forceinline__ int part_list(const PartGeom<T>& G, const T* s_thr, T
     return s;
 }
 
+// Wide form: the cell of one coordinate on axis d, for classification only (uniform axes by formula, the others from
+// the node records through the bucket table, global memory / L1), and the list of a point from its first two.
+template <class T>
+__device__ __forceinline__ int part_axis_cell(const Params<T>& P, int d, T x, bool wrap) {
+    if (wrap && !(P.g0[d] <= x && x <= P.gl[d])) x = wrap_coord(x, P.g0[d], P.gl[d]);
+    if (!(x == x)) return 0;
+    int k;
+    if (P.flags[d] & kAxisUniform) k = to_int_sat((x - P.g0[d]) * P.inv_h[d]);
+    else k = count_less(load_axis<T>(P, P.pack, d), x) - 1;
+    return max(0, min(k, P.L[d] - 2));
+}
+template <class T>
+__device__ __forceinline__ int part_list_wide(const Params<T>& P, const PartGeom<T>& G, T x, T y) {
+    const unsigned flat = (unsigned)part_axis_cell(P, 0, x, G.wrap != 0) * G.wide_cells1 + (unsigned)part_axis_cell(P, 1, y, G.wrap != 0);
+    return (int)min(flat / G.wide_per, (unsigned)G.lists - 1u);
+}
+
 // Measured alternative (1e9 random points, 256^3 f64): the three columns brought in by per-thread 8-byte cp.async into
 // the slots they were read from and permuted in place after a barrier -- no coordinate registers, every request out
 // before the first wait -- ran the kernel at 3.02 ms per 2^28 points against 2.73 ms for this form.
 template <class T>
-__global__ void __launch_bounds__(kPartThreads, kPartScatterCtas) part_scatter_kernel(const __grid_constant__ Params<T> P,
+__global__ void __launch_bounds__(kPartThreads, 2) part_scatter_kernel(const __grid_constant__ Params<T> P,
                                                                        const __grid_constant__ PartGeom<T> G) {
     extern __shared__ __align__(128) unsigned char part_smem[];
     T* s_rec = reinterpret_cast<T*>(part_smem);  // [3][kPartChunk]
@@ -118,9 +130,6 @@ __global__ void __launch_bounds__(kPartThreads, kPartScatterCtas) part_scatter_k
     // the first two columns of a chunk are requested while the previous chunk drains (its bulk stores read the staged
     // records, then a barrier): one of the two DRAM round trips of a chunk is off the critical path
     T x[kPartPer], y[kPartPer];
-#if NINT_PART_PREFETCH_Z
-    T z[kPartPer];
-#endif
     auto request_xy = [&](unsigned c) {
         const unsigned base = c << kPartChunkShift;
 #pragma unroll
@@ -133,13 +142,6 @@ __global__ void __launch_bounds__(kPartThreads, kPartScatterCtas) part_scatter_k
             const unsigned i = base + r * kPartThreads + t;
             y[r] = (c < G.nchunks && i < n) ? ld_stream(P.coords[1] + (size_t)i * P.coord_stride) : T(0);
         }
-#if NINT_PART_PREFETCH_Z
-#pragma unroll
-        for (int r = 0; r < kPartPer; ++r) {
-            const unsigned i = base + r * kPartThreads + t;
-            z[r] = (c < G.nchunks && i < n) ? ld_stream(P.coords[2] + (size_t)i * P.coord_stride) : T(0);
-        }
-#endif
     };
     request_xy(blockIdx.x);
     for (unsigned c = blockIdx.x; c < G.nchunks; c += gridDim.x) {
@@ -185,14 +187,12 @@ __global__ void __launch_bounds__(kPartThreads, kPartScatterCtas) part_scatter_k
         }
     }
     {
-#if !NINT_PART_PREFETCH_Z
         T z[kPartPer];
 #pragma unroll
         for (int r = 0; r < kPartPer; ++r) {
             const unsigned i = base + r * kPartThreads + t;
             z[r] = (i < n) ? ld_stream(P.coords[2] + (size_t)i * P.coord_stride) : T(0);
         }
-#endif
 #pragma unroll
         for (int r = 0; r < kPartPer; ++r) {
             const unsigned i = base + r * kPartThreads + t;
@@ -205,6 +205,141 @@ __global__ void __launch_bounds__(kPartThreads, kPartScatterCtas) part_scatter_k
     if (t == 0) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) bulk_store(G.rec[d] + base, s_rec + d * kPartChunk, kPartChunk * (unsigned)sizeof(T));
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    request_xy(c + gridDim.x);
+    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();  // the staged chunk has been read: the next one may be written
+    }
+}
+
+// The same for four and five axes: N columns, up to 128 lists by the flattened (axis 0, axis 1) cell index (a copy rather
+// than a template argument of the kernel above: the 3-D f64 kernel sits at 64 registers and spilled in the merged form).
+template <class T, int N>
+__global__ void __launch_bounds__(kPartThreads, 2) part_scatter_wide_kernel(const __grid_constant__ Params<T> P,
+                                                                       const __grid_constant__ PartGeom<T> G) {
+    static_assert(N >= 4 && N <= kPartMaxDim, "wide scatter: four or five axes");
+    constexpr bool WIDE = true;
+    constexpr int kLists = WIDE ? kPartMaxListsWide : kPartMaxLists;
+    extern __shared__ __align__(128) unsigned char part_smem[];
+    T* s_rec = reinterpret_cast<T*>(part_smem);  // [N][kPartChunk]
+    __shared__ unsigned s_cnt[kLists];
+    __shared__ unsigned s_off[kLists];
+    __shared__ T s_thr[kPartMaxLists];
+    if (P.mode_flag != nullptr && *P.mode_flag != P.mode_want) return;
+    const unsigned t = threadIdx.x, lane = t & 31u, lt = (1u << lane) - 1u;
+    const unsigned n = (unsigned)P.n;
+    if (t < (unsigned)kPartMaxLists) s_thr[t] = G.thr[t];
+    if (blockIdx.x == 0 && t == 0) *G.ticket = 0u;
+    // resident CTAs walk the chunks (a CTA per chunk would be 65536 CTAs per segment, which cost a coherent batch --
+    // where this launch only reads the verdict and returns -- 25 us each time)
+    // the first two columns of a chunk are requested while the previous chunk drains (its bulk stores read the staged
+    // records, then a barrier): one of the two DRAM round trips of a chunk is off the critical path
+    T x[kPartPer], y[kPartPer];
+    auto request_xy = [&](unsigned c) {
+        const unsigned base = c << kPartChunkShift;
+#pragma unroll
+        for (int r = 0; r < kPartPer; ++r) {
+            const unsigned i = base + r * kPartThreads + t;
+            x[r] = (c < G.nchunks && i < n) ? ld_stream(P.coords[0] + (size_t)i * P.coord_stride) : quiet_nan<T>();
+        }
+#pragma unroll
+        for (int r = 0; r < kPartPer; ++r) {
+            const unsigned i = base + r * kPartThreads + t;
+            y[r] = (c < G.nchunks && i < n) ? ld_stream(P.coords[1] + (size_t)i * P.coord_stride) : T(0);
+        }
+    };
+    request_xy(blockIdx.x);
+    for (unsigned c = blockIdx.x; c < G.nchunks; c += gridDim.x) {
+    const unsigned base = c << kPartChunkShift;
+    if (t < (unsigned)kLists) s_cnt[t] = 0u;
+    __syncthreads();
+    // place inside the list: one shared-memory atomic per group of lanes with the same list
+    unsigned pk[kPartPer];  // place inside the list | list << 16, then the place inside the chunk
+#pragma unroll
+    for (int r = 0; r < kPartPer; ++r) {
+        const unsigned i = base + r * kPartThreads + t;
+        unsigned s;
+        if constexpr (WIDE) s = (i < n) ? (unsigned)part_list_wide(P, G, x[r], y[r]) : 255u;
+        else s = (i < n) ? (unsigned)part_list(G, s_thr, x[r]) : 255u;
+        const unsigned m = __match_any_sync(0xffffffffu, s);
+        const int leader = __ffs(m) - 1;
+        unsigned b = 0u;
+        if ((int)lane == leader && s != 255u) b = atomicAdd(&s_cnt[s], (unsigned)__popc(m));
+        b = __shfl_sync(0xffffffffu, b, leader);
+        pk[r] = (b + __popc(m & lt)) | (s << 16);
+    }
+    __syncthreads();
+    if (t < 32u) {
+        if constexpr (!WIDE) {
+            const unsigned cnt = ((int)t < G.lists) ? s_cnt[t] : 0u;
+            unsigned incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)lane >= d) incl += up;
+            }
+            s_off[t] = incl - cnt;
+            NINT_ASSERT(incl <= kPartChunk);
+            if ((int)t < G.lists) G.runs[(size_t)t * G.run_stride + c] = (incl - cnt) | (cnt << 16);
+        } else {  // four lists per lane
+            constexpr int kEach = kLists / 32;
+            unsigned cnt[kEach], sum = 0u;
+#pragma unroll
+            for (int e = 0; e < kEach; ++e) {
+                const int k = (int)t * kEach + e;
+                cnt[e] = (k < G.lists) ? s_cnt[k] : 0u;
+                sum += cnt[e];
+            }
+            unsigned incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)lane >= d) incl += up;
+            }
+            NINT_ASSERT(incl <= kPartChunk);
+            unsigned start = incl - sum;
+#pragma unroll
+            for (int e = 0; e < kEach; ++e) {
+                const int k = (int)t * kEach + e;
+                s_off[k] = start;
+                if (k < G.lists) G.runs[(size_t)k * G.run_stride + c] = start | (cnt[e] << 16);
+                start += cnt[e];
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kPartPer; ++r) {
+        const unsigned i = base + r * kPartThreads + t;
+        if (i < n) {
+            pk[r] = s_off[pk[r] >> 16] + (pk[r] & 0xffffu);
+            NINT_ASSERT(pk[r] < kPartChunk);
+            s_rec[pk[r]] = x[r];
+            s_rec[kPartChunk + pk[r]] = y[r];
+            G.pos[i] = (unsigned short)pk[r];
+        }
+    }
+#pragma unroll 1
+    for (int d = 2; d < N; ++d) {
+        T z[kPartPer];
+#pragma unroll
+        for (int r = 0; r < kPartPer; ++r) {
+            const unsigned i = base + r * kPartThreads + t;
+            z[r] = (i < n) ? ld_stream(P.coords[d] + (size_t)i * P.coord_stride) : T(0);
+        }
+#pragma unroll
+        for (int r = 0; r < kPartPer; ++r) {
+            const unsigned i = base + r * kPartThreads + t;
+            if (i < n) s_rec[d * kPartChunk + pk[r]] = z[r];
+        }
+    }
+    // whole chunks leave (the lists are allocated in whole chunks; what lies beyond a ragged chunk's points is never read)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (t == 0) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) bulk_store(G.rec[d] + base, s_rec + d * kPartChunk, kPartChunk * (unsigned)sizeof(T));
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     request_xy(c + gridDim.x);
@@ -244,82 +379,13 @@ __device__ __forceinline__ T part_point(const Params<T>& P, const unsigned char*
     return result;
 }
 
-// part_point in phases, for the kernel form that evaluates several groups per trip: the weights of every group (these
-// contain branches: the division's slow path, the retry of a non-uniform axis), then all gathers, then the blends.
-// The operations on a point's data are those of fast_point (nint_device.cuh), in the same order.
-template <class T, bool IS_ND, bool UNI, bool FIRST>
-__device__ __forceinline__ bool part_weights_table(const Params<T>& P, const unsigned char* pack, const T (&p)[3], int (&k)[3], T (&t)[3]) {
-    constexpr bool kCollapse = IS_ND;
-    bool ok = true;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        const unsigned* guess = UNI ? nullptr : reinterpret_cast<const unsigned*>(pack + P.guess_off[d]);
-        ok = guess_cell<T, UNI>(load_axis<T>(P, pack, d), guess, p[d], k[d]) && ok;
-    }
-    if (!ok) return false;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        T a, w, r;
-        ok = verify_cell_linear<T, kCollapse, FIRST>(load_axis<T>(P, pack, d), p[d], k[d], a, w, r) && ok;
-        t[d] = div_markstein<T>(a, w, r);
-    }
-    if (!UNI && !ok) {
-        ok = true;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            T a, w, r;
-            ok = verify_linear_retry<T, kCollapse, FIRST, UNI>(load_axis<T>(P, pack, d), p[d], k[d], a, w, r) && ok;
-            t[d] = div_markstein<T>(a, w, r);
-        }
-    }
-    return ok;
-}
-// false: the point takes the general path (its gather is still issued, from cell 0)
-template <class T, bool IS_ND, int PRE, bool UNI, bool ANA>
-__device__ __forceinline__ bool part_weights(const Params<T>& P, const unsigned char* pack, const Point<T, 3>& q, unsigned& cell, T (&t)[3]) {
-    T p[3];
-    bool oob = false;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        p[d] = (PRE == kPreClamp) ? clamp_coord(q.v[d], P.g0[d], P.gl[d]) : q.v[d];
-        if (PRE == kPreWrap) oob = oob || !(P.g0[d] <= q.v[d] && q.v[d] <= P.gl[d]);
-    }
-    if (PRE == kPreWrap) {
-        if (oob) {
-            const Point<T, 3> w = wrap_point<T, 3>(P, q);
-#pragma unroll
-            for (int d = 0; d < 3; ++d) p[d] = w.v[d];
-        }
-    }
-    int k[3] = {0, 0, 0};
-#pragma unroll
-    for (int d = 0; d < 3; ++d) t[d] = T(0);
-    bool ok;
-    if constexpr (ANA) ok = fast_weights_analytic<T, 3, IS_ND, PRE == kPreClamp>(P, p, k, t);
-    else ok = part_weights_table<T, IS_ND, UNI, PRE == kPreClamp>(P, pack, p, k, t);
-    cell = 0u;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) cell += (unsigned)k[d] * (unsigned)P.cstride[d];
-    if (!ok) cell = 0u;
-    NINT_ASSERT((unsigned long long)cell < P.ncells);
-    return ok;
-}
-template <class T, int N, bool IS_ND>
-__device__ __forceinline__ T part_general(const Params<T>& P, const unsigned char* pack, const Point<T, N>& q, unsigned& status) {
-    const Outcome<T> o = general_point<T, N, IS_ND, NINT_LINEAR>(P, pack, q);
-    status = o.status;
-    return (status != NINT_STATUS_OK) ? quiet_nan<T>() : o.value;
-}
-
-// f64: 80 registers, 3 CTAs; f32: 64 registers, 4 CTAs (measured: 17.4 -> 16.3 ms; f64 at 64 registers spills: 29.5 ms)
+// f64: 80 registers, 3 CTAs; f32: 64 registers, 4 CTAs (measured: 17.4 -> 16.3 ms; f64 at 64 registers spills: 29.5 ms);
+// four and five axes as the single pass has them (2^N corners in registers)
 #ifndef NINT_PART_CTAS
-#define NINT_PART_CTAS (sizeof(T) == 4 ? 4 : 3)
+#define NINT_PART_CTAS (N == 3 ? (sizeof(T) == 4 ? 4 : 3) : ((N == 4 || sizeof(T) == 4) ? 2 : 1))
 #endif
 #ifndef NINT_PART_AHEAD
 #define NINT_PART_AHEAD 2
-#endif
-#ifndef NINT_PART_ILP
-#define NINT_PART_ILP 1
 #endif
 
 constexpr unsigned kPartTicket = 4;  // chunks per ticket of the evaluate kernel
@@ -332,7 +398,7 @@ constexpr unsigned kPartTicket = 4;  // chunks per ticket of the evaluate kernel
 // groups 25.6 ms, of three 27.6 ms (80 registers, 3 CTAs); 4 CTAs at 64 registers 26.9 (one ahead) / 29.5 ms (two,
 // spills).  A per-warp ring in shared memory filled by TMA bulk copies (three 256-byte requests per group, mbarrier per
 // stage, 4 CTAs without spills) measured 27.5 ms with 4 stages, 28.1 with 3, 38.8 with 6.
-template <class T, bool IS_ND, int PRE, bool UNI, bool ANA>
+template <class T, bool IS_ND, int PRE, bool UNI, bool ANA, int N = 3>
 __global__ void __launch_bounds__(kBlock, NINT_PART_CTAS) part_eval_kernel(const __grid_constant__ Params<T> P,
                                                                            const __grid_constant__ PartGeom<T> G) {
     extern __shared__ __align__(16) unsigned char smem_pack[];
@@ -355,22 +421,6 @@ __global__ void __launch_bounds__(kBlock, NINT_PART_CTAS) part_eval_kernel(const
         const unsigned k = t / tpl;
         const unsigned c = (t - k * tpl) * kPartTicket + lane;
         return (lane < kPartTicket && c < G.nchunks) ? __ldg(G.runs + (size_t)k * G.run_stride + c) : 0u;
-    };
-    // The first gathers of a list find nothing of its slab in L2: one lane in thirteen then waits for DRAM, which is
-    // nearly every group of 32.  The warps entering a list (they all do at about the same time) ask for the slab
-    // piece by piece instead -- sequential reads, ~10 us for 40 MB -- so the groups behind them hit.
-    auto prefetch_piece = [&](unsigned t) {
-        const unsigned k = t / tpl;
-        const unsigned long long off = (unsigned long long)(t - k * tpl) * G.pf_piece;
-        if (off < G.slab_bytes) {
-            const unsigned long long at = (unsigned long long)k * G.slab_bytes + off;
-            if (at < G.table_bytes) {
-                unsigned long long len = G.slab_bytes - off;
-                if (len > G.pf_piece) len = G.pf_piece;
-                if (len > G.table_bytes - at) len = G.table_bytes - at;
-                bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(P.cells) + at, (unsigned)len & ~15u, pol);
-            }
-        }
     };
     unsigned raw = draw();
     unsigned t_next = __shfl_sync(0xffffffffu, raw, 0);
@@ -395,7 +445,6 @@ __global__ void __launch_bounds__(kBlock, NINT_PART_CTAS) part_eval_kernel(const
                 if (t_next >= total) return false;
                 ent = ent_next;
                 cb = (t_next % tpl) * kPartTicket;
-                if (G.pf_piece != 0u && lane == 0u) prefetch_piece(t_next);
                 j = 0u;
                 raw = draw();
                 pending = true;
@@ -407,9 +456,9 @@ __global__ void __launch_bounds__(kBlock, NINT_PART_CTAS) part_eval_kernel(const
         }
         return true;
     };
-    auto fetch = [&](unsigned idx, Point<T, 3>& q) {
+    auto fetch = [&](unsigned idx, Point<T, N>& q) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) q.v[d] = ld_stream(G.rec[d] + idx);
+        for (int d = 0; d < N; ++d) q.v[d] = ld_stream(G.rec[d] + idx);
     };
     // The f64 kernel sits at the edge of its 80 registers and is sensitive to the shape of this loop.  Measured on the
     // headline batch (25.8 ms in this form): an `inflight` counter and idx == ~0u for idle lanes instead of the flags
@@ -418,11 +467,9 @@ __global__ void __launch_bounds__(kBlock, NINT_PART_CTAS) part_eval_kernel(const
     // kAhead groups of records are in flight beyond the one being evaluated (a record load is a DRAM round trip, and a
     // group's evaluation -- two dependent L2 gathers -- is shorter than that under load)
     constexpr int kAhead = NINT_PART_AHEAD;
-    constexpr int kIlp = NINT_PART_ILP;  // groups evaluated together: their gathers are in flight at the same time
-    constexpr int kSlots = kAhead + kIlp;
-    Point<T, 3> q[kSlots];
-    unsigned idx[kSlots];
-    bool live[kSlots], has[kSlots];
+    Point<T, N> q[kAhead + 1];
+    unsigned idx[kAhead + 1];
+    bool live[kAhead + 1], has[kAhead + 1];
     bool done = false;
     auto load_slot = [&](int s) {
         has[s] = !done && advance();
@@ -437,73 +484,20 @@ __global__ void __launch_bounds__(kBlock, NINT_PART_CTAS) part_eval_kernel(const
     };
 #pragma unroll
     for (int s = 0; s < kAhead; ++s) load_slot(s);
-    if constexpr (kIlp == 1) {
-        while (has[0]) {
-            load_slot(kAhead);
-            if (live[0]) {
-                unsigned status;
-                const T res = part_point<T, 3, IS_ND, PRE, UNI, ANA>(P, pack, pol, q[0], status);
-                st_stream(G.vals + idx[0], res);
-                G.stat[idx[0]] = (uint8_t)status;
-            }
-#pragma unroll
-            for (int s = 0; s < kAhead; ++s) {
-                q[s] = q[s + 1];
-                idx[s] = idx[s + 1];
-                live[s] = live[s + 1];
-                has[s] = has[s + 1];
-            }
+    while (has[0]) {
+        load_slot(kAhead);
+        if (live[0]) {
+            unsigned status;
+            const T res = part_point<T, N, IS_ND, PRE, UNI, ANA>(P, pack, pol, q[0], status);
+            st_stream(G.vals + idx[0], res);
+            G.stat[idx[0]] = (uint8_t)status;
         }
-    } else {
-        // kIlp groups per trip: every fast path first (branch-free up to its verdict, so the gathers of all of them are
-        // issued before the first blend waits), then the general path for whatever declined
-        while (has[0]) {
 #pragma unroll
-            for (int s = 0; s < kIlp; ++s) load_slot(kAhead + s);
-            T res[kIlp];
-            bool ok[kIlp];
-            unsigned cell[kIlp];
-            T t[kIlp][3];
-            T cube[kIlp][8];
-#pragma unroll
-            for (int s = 0; s < kIlp; ++s) {  // idle lanes evaluate the grid's first node
-                if (!live[s]) {
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) q[s].v[d] = P.g0[d];
-                }
-                ok[s] = part_weights<T, IS_ND, PRE, UNI, ANA>(P, pack, q[s], cell[s], t[s]);
-            }
-#pragma unroll
-            for (int s = 0; s < kIlp; ++s) ld_cells_keep<8>(P.cells + (size_t)cell[s] * 8, pol, cube[s]);
-#pragma unroll
-            for (int s = 0; s < kIlp; ++s) {
-                // reduce axis 0 first, then 1, 2: v_l * (1 - t) + v_u * t, each operation rounded separately (fast_point)
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    const int half = 1 << (2 - d);
-                    const T td = t[s][d];
-                    const T sd = T(1) - td;
-#pragma unroll
-                    for (int j = 0; j < half; ++j) cube[s][j] = cube[s][j] * sd + cube[s][half + j] * td;
-                }
-                res[s] = cube[s][0];
-            }
-#pragma unroll
-            for (int s = 0; s < kIlp; ++s) {
-                if (live[s]) {
-                    unsigned status = NINT_STATUS_OK;
-                    if (!ok[s]) res[s] = part_general<T, 3, IS_ND>(P, pack, q[s], status);
-                    st_stream(G.vals + idx[s], res[s]);
-                    G.stat[idx[s]] = (uint8_t)status;
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < kAhead; ++s) {
-                q[s] = q[s + kIlp];
-                idx[s] = idx[s + kIlp];
-                live[s] = live[s + kIlp];
-                has[s] = has[s + kIlp];
-            }
+        for (int s = 0; s < kAhead; ++s) {
+            q[s] = q[s + 1];
+            idx[s] = idx[s + 1];
+            live[s] = live[s + 1];
+            has[s] = has[s + 1];
         }
     }
 }
@@ -513,7 +507,7 @@ template <class T>
 constexpr unsigned part_merge_smem() { return 2u * kPartChunk * ((unsigned)sizeof(T) + 1u); }
 
 template <class T>
-__global__ void __launch_bounds__(kPartThreads, kPartMergeCtas) part_merge_kernel(const __grid_constant__ Params<T> P,
+__global__ void __launch_bounds__(kPartThreads, 3) part_merge_kernel(const __grid_constant__ Params<T> P,
                                                                      const __grid_constant__ PartGeom<T> G) {
     extern __shared__ __align__(128) unsigned char part_smem[];
     constexpr unsigned kBuf = kPartChunk * ((unsigned)sizeof(T) + 1u);  // results, then status bytes
@@ -592,6 +586,7 @@ struct PartLaunch {
     int is_nd;
     int all_uniform;
     int all_analytic;  // every axis is uniform with nodes exactly g0 + k * h: the evaluate kernel computes them
+    int ndim;             // 3; 4 or 5 with the wide scatter (InterpND)
     int sm_count;
     unsigned smem_bytes;  // axis pack
     int grid_div, merge_div;  // tuning: > 0 = one CTA per that many chunks in the scatter / merge kernel instead of resident CTAs

@@ -533,6 +533,51 @@ def test_slab_list_route(monkeypatch):
         assert _lib.lib().nint_last_incoherent_route(g._h) == 3
 
 
+def test_slab_list_route_nd(monkeypatch):
+    # The same route for InterpND with four and five axes (default there under Extrapolate::Wrap on tables beyond L2):
+    # N columns, lists by slab of the flattened (axis 0, axis 1) cell index -- up to 128 of them --, cells found from
+    # the axis records.  Forced on small tables; NINT_COMPACT=0 sends Fill and Error through it as well.
+    from gpu_util import assert_same, expected_info, gpu_eval, make_pair
+
+    from ninterp_b200 import _lib
+
+    monkeypatch.setenv("NINT_SLAB_MIN_BYTES", "0")
+    monkeypatch.setenv("NINT_SLAB_MIN_POINTS", "0")
+    monkeypatch.setenv("NINT_ROUTE", "part")
+    monkeypatch.setenv("NINT_COMPACT", "0")
+    monkeypatch.setenv("NINT_PROBE_SHIFT", "0")
+    rng = np.random.default_rng(778)
+    for lens, dtype, mode, slab_mb, seg_shift, n in [((7, 6, 9, 8), np.float64, "nonuniform", 0.02, 15, 200_001),
+                                                     ((6, 5, 7, 6, 8), np.float32, "nonuniform", 0.05, 28, 200_001),
+                                                     ((13, 12, 4, 4, 4), np.float32, "uniform", 0.007, 16, 150_000),
+                                                     ((5, 6, 5, 6, 5), np.float64, "uniform", 0.1, 28, 4_097)]:
+        monkeypatch.setenv("NINT_PART_SLAB_MB", str(slab_mb))
+        monkeypatch.setenv("NINT_PART_SEG_SHIFT", str(seg_shift))
+        monkeypatch.setenv("NINT_PROBE_MAX_DISTINCT", str(min(int(np.prod([l - 1 for l in lens])) // 3, 2000)))
+        axes = _axes(rng, lens, dtype, mode)
+        values = rng.uniform(-1, 1, lens).astype(dtype)
+        for extrap in (WRAP, CLAMP, ENABLE, ERROR, FILL):
+            g, o = make_pair(ND, axes, values, LIN, extrap, fill=-2.5, dtype=dtype)
+            cols = _queries(rng, axes, n, dtype, 0.3 if extrap == WRAP else 0.05)
+            for d in range(len(lens)):
+                a = np.asarray(axes[d], dtype=dtype)
+                special = np.concatenate([a, np.nextafter(a, dtype(np.inf)), np.nextafter(a, dtype(-np.inf)),
+                                          np.array([np.nan, np.inf, -np.inf], dtype=dtype)])
+                where = rng.choice(n, special.size, replace=False)
+                cols[d][where] = special
+            want, st_want = o.eval(cols, nthreads=O.max_threads())
+            got, st, info = gpu_eval(g, cols)
+            assert_same(got, st, want, st_want, f"slab lists N-D random {lens} {extrap}")
+            assert info == expected_info(st_want)
+            assert _lib.lib().nint_last_query_order(g._h) == 2
+            assert _lib.lib().nint_last_incoherent_route(g._h) == 3
+            got, st, _ = gpu_eval(g, cols, aos=True)
+            assert_same(got, st, want, st_want, f"slab lists N-D aos {lens} {extrap}")
+            order = np.lexsort([np.searchsorted(axes[d], cols[d]) for d in reversed(range(len(lens)))])
+            got, st, info = gpu_eval(g, [c[order] for c in cols])
+            assert_same(got, st, want[order], st_want[order], f"slab lists N-D sorted {lens} {extrap}")
+
+
 def test_concurrent_batches_on_one_handle(monkeypatch):
     # include/ninterp_cuda.h: a handle is immutable during batch calls, so several host threads may evaluate
     # batches on their own streams at once -- on the single-pass route and on the probed one (order flag ring)

@@ -92,6 +92,8 @@ def main():
     run("slab lists", FIXED, (37, 35, 70), np.float64, LIN, ERROR, n, rng, env=part)
     run("slab lists wrap aos", FIXED, (40, 9, 8), np.float64, LIN, WRAP, n, rng, uniform="analytic", env=dict(part, NINT_PART_SLAB_MB="0.008"), aos=True)
     run("slab lists f32 nd", ND, (21, 40, 36), np.float32, LIN, FILL, 50_001, rng, env=part)
+    run("slab lists 5-d f32 wrap", ND, (6, 5, 7, 4, 8), np.float32, LIN, WRAP, 50_001, rng, env=dict(part, NINT_PART_SLAB_MB="0.02"))
+    run("slab lists 4-d f64 aos", ND, (10, 9, 12, 8), np.float64, LIN, CLAMP, n, rng, env=part, aos=True)
     run("length-1 axes nd", ND, (1, 6, 1, 5), np.float64, LIN, CLAMP, n, rng)
     run("length-2 axes", FIXED, (2, 2, 2), np.float64, LIN, ENABLE, n, rng)
     run("1d left", FIXED, (33,), np.float64, LEFT, ERROR, n, rng)
