@@ -725,6 +725,21 @@ __device__ __forceinline__ bool fast_weights_analytic(const Params<T>& P, const 
     return ok;
 }
 
+// The blend of the 2^N corners with the stage widths as compile-time constants.  Four and five axes: with the loop form
+// below (bound 1 << (N - 1 - d) inside an unrolled loop over d) the compiler kept the 16- and 8-wide stages as loops over
+// a copy of the corners in local memory (ncu: STL.128 / LDL.128 around the gather, 256 bytes of stack).
+template <class T, int N, int D = 0>
+__device__ __forceinline__ void blend_stages(T (&cube)[1 << N], const T (&t)[N]) {
+    if constexpr (D < N) {
+        constexpr int half = 1 << (N - 1 - D);
+        const T td = t[D];
+        const T sd = T(1) - td;
+#pragma unroll
+        for (int j = 0; j < half; ++j) cube[j] = cube[j] * sd + cube[half + j] * td;
+        blend_stages<T, N, D + 1>(cube, t);
+    }
+}
+
 // The whole fast path for one point; false when anything about it needs the general path.
 // PLAIN: 0 = Linear gathers from the cell-packed table when there is one, 1 = from the plain table (slab passes),
 // 2 = from the cell-packed table with the L2 policy `pol` (slab lists; 3-D only)
@@ -861,13 +876,17 @@ __device__ __forceinline__ bool fast_point(const Params<T>& P, const unsigned ch
             gather_rows<T, N>(P.values + base, step, pol, false, cube);
         }
         // reduce axis 0 first, then 1, ...: v_l * (1 - t) + v_u * t, each op rounded separately
+        if constexpr (N == 4 || N == 5) {  // (six axes and more: 2^N corners do not fit the register file either way)
+            blend_stages<T, N>(cube, t);
+        } else {
 #pragma unroll
-        for (int d = 0; d < N; ++d) {
-            const int half = 1 << (N - 1 - d);
-            const T td = t[d];
-            const T sd = T(1) - td;
+            for (int d = 0; d < N; ++d) {
+                const int half = 1 << (N - 1 - d);
+                const T td = t[d];
+                const T sd = T(1) - td;
 #pragma unroll
-            for (int j = 0; j < half; ++j) cube[j] = cube[j] * sd + cube[half + j] * td;
+                for (int j = 0; j < half; ++j) cube[j] = cube[j] * sd + cube[half + j] * td;
+            }
         }
         result = cube[0];
         return ok;

@@ -380,9 +380,9 @@ __device__ __forceinline__ T part_point(const Params<T>& P, const unsigned char*
 }
 
 // f64: 80 registers, 3 CTAs; f32: 64 registers, 4 CTAs (measured: 17.4 -> 16.3 ms; f64 at 64 registers spills: 29.5 ms);
-// four and five axes as the single pass has them (2^N corners in registers)
+// four and five axes, f32: 3 CTAs (32^5 under Wrap, 2e8 points: 15.6 -> 13.2 ms against 2 CTAs), f64: what 2^N corners leave
 #ifndef NINT_PART_CTAS
-#define NINT_PART_CTAS (N == 3 ? (sizeof(T) == 4 ? 4 : 3) : ((N == 4 || sizeof(T) == 4) ? 2 : 1))
+#define NINT_PART_CTAS (N == 3 ? (sizeof(T) == 4 ? 4 : 3) : (sizeof(T) == 4 ? 3 : (N == 4 ? 2 : 1)))
 #endif
 #ifndef NINT_PART_AHEAD
 #define NINT_PART_AHEAD 2

@@ -101,6 +101,10 @@ __device__ __forceinline__ bool fast_weights(const Params<T>& P, const unsigned 
 // three/strategies.rs:37-49 (and two/, n/): reduce axis 0 first, v_l * (1 - t) + v_u * t, every op rounded separately.
 template <class T, int N>
 __device__ __forceinline__ T blend_cube(T (&cube)[1 << N], const T (&t)[N]) {
+    if constexpr (N == 4 || N == 5) {  // stage widths as constants: the loop form below left the corners in local memory
+        blend_stages<T, N>(cube, t);
+        return cube[0];
+    }
 #pragma unroll
     for (int d = 0; d < N; ++d) {
         const int half = 1 << (N - 1 - d);

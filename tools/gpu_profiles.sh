@@ -21,7 +21,8 @@ cap tilesorted "interp_kernel" 1 $P --case tilesorted --points 1e9 --launches 1
 cap tiles "tile_" 2 env NINT_ROUTE=tile $P --case random --points 2.6e8 --launches 1
 cap fused1d "interp1d_fused" 1 $P --case 1d --points 4e8 --launches 1
 cap nd5fill "slab_kernel" 1 $P --case nd5 --extrap fill --points 2e8 --launches 1
-cap nd5wrap "interp_kernel" 1 $P --case nd5 --points 2e8 --launches 1
+cap nd5wrap "interp_kernel" 1 env NINT_PART_ND=0 $P --case nd5 --points 2e8 --launches 1
+cap nd5wraplists "part_" 3 $P --case nd5 --points 2e8 --launches 1
 cap near2d "interp_kernel" 1 $P --case 2d --strategy nearest --points 1e8 --launches 1
 cap lin2d "interp_kernel" 1 $P --case 2d --points 1e8 --launches 1
 [ -n "$ONLY" ] || python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/r2p_bench_plain.log 2>&1 &&

@@ -14,7 +14,7 @@ import bench  # noqa: E402
 NAMES = {"lists": "interp3d_linear_f64_256cubed_random_slab_lists", "slab": "interp3d_linear_f64_256cubed_random_slab_passes", "tiles": "interp3d_linear_f64_256cubed_random_binned_tiles_2.6e8_points",
          "sorted": "interp3d_linear_f64_256cubed_cell_sorted", "tilesorted": "interp3d_linear_f64_256cubed_tile_sorted_8cubed",
          "fused1d": "interp1d_linear_f64_1000_nodes_fused_4e8_points", "nd5fill": "interpnd5_linear_f32_32pow5_fill_inrange_compaction",
-         "nd5wrap": "interpnd5_linear_f32_32pow5_wrap", "near2d": "interp2d_nearest_f64_2048sq_clamp", "lin2d": "interp2d_linear_f64_2048sq_clamp"}
+         "nd5wrap": "interpnd5_linear_f32_32pow5_wrap", "nd5wraplists": "interpnd5_linear_f32_32pow5_wrap_slab_lists", "near2d": "interp2d_nearest_f64_2048sq_clamp", "lin2d": "interp2d_linear_f64_2048sq_clamp"}
 
 
 def kernels(path):
@@ -65,8 +65,12 @@ def main():
         (prof / "r2_ncu_launch_list_bench_summary.txt").write_text("\n".join(lines) + "\n")
     # DRAM traffic per batch call
     tot = lambda k: k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"]
-    slab, tiles, srt, lists = (kernels(out / f"r2p_summary_{k}.txt") for k in ("slab", "tiles", "sorted", "lists"))
     old = json.load(open(prof / "traffic.json"))
+    have = all((out / f"r2p_summary_{k}.txt").exists() for k in ("slab", "tiles", "sorted", "lists"))
+    if not have:
+        print("not every route was captured: traffic.json left as it is")
+        return
+    slab, tiles, srt, lists = (kernels(out / f"r2p_summary_{k}.txt") for k in ("slab", "tiles", "sorted", "lists"))
     tj = {"note": "dram__bytes_read.sum + dram__bytes_write.sum from `ncu --set full` captures (profiles/r2_ncu_full_*.txt), per batch call of "
                   "1e9 points: the slab lists are scaled from a 2.6e8-point capture (scatter + evaluate + merge); the slab route is the order "
                   "probe + 3 slab_kernel passes; the binned-tiles figure is scaled from a 2.6e8-point capture (bin + evaluate); the single-pass figure on random queries is the round-1 capture (that kernel's random path is unchanged)",
