@@ -925,8 +925,8 @@ int part_lists(const nint_handle* h, size_t n, int* cells_per_list) {
     const char* e_mb = std::getenv("NINT_PART_SLAB_MB");
     // four and five axes: with up to 128 lists the runs of a chunk are short (a third of the lanes idle at 40 MiB on 32^5),
     // and the evaluate kernel is bound by its front-end, not by L2 hits: larger slabs measured faster (2e8 points, 32^5 f32,
-    // Wrap: 40 MiB 15.6 ms, 96 MiB 14.1 ms)
-    const double slab = (e_mb ? std::atof(e_mb) : (wide ? 96.0 : 40.0)) * 1024.0 * 1024.0;
+    // Wrap, 3 CTAs: 96 MiB 12.1 ms, 128 11.9, 160 11.8, 224 11.6, 320 12.3, 640 16.5)
+    const double slab = (e_mb ? std::atof(e_mb) : (wide ? 160.0 : 40.0)) * 1024.0 * 1024.0;
     // rows of the slab index: axis-0 cells, or (axis-0 cell, axis-1 cell) pairs
     const long long rows = wide ? ((long long)h->axis_len[0] - 1) * ((long long)h->axis_len[1] - 1) : (long long)h->axis_len[0] - 1;
     const double row_bytes = packed / (double)rows;  // bytes of the packed table per row
