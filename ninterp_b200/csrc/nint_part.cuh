@@ -45,6 +45,9 @@
 
 namespace nint {
 
+#ifndef NINT_PART_EARLY_X
+#define NINT_PART_EARLY_X 0
+#endif
 constexpr unsigned kPartChunkShift = 12;
 constexpr unsigned kPartChunk = 1u << kPartChunkShift;  // points per chunk: positions and run bounds fit 16 bits
 constexpr int kPartThreads = 512;
@@ -130,20 +133,24 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_scatter_kernel(const __g
     // the first two columns of a chunk are requested while the previous chunk drains (its bulk stores read the staged
     // records, then a barrier): one of the two DRAM round trips of a chunk is off the critical path
     T x[kPartPer], y[kPartPer];
-    auto request_xy = [&](unsigned c) {
+    auto request_x = [&](unsigned c) {
         const unsigned base = c << kPartChunkShift;
 #pragma unroll
         for (int r = 0; r < kPartPer; ++r) {
             const unsigned i = base + r * kPartThreads + t;
             x[r] = (c < G.nchunks && i < n) ? ld_stream(P.coords[0] + (size_t)i * P.coord_stride) : quiet_nan<T>();
         }
+    };
+    auto request_y = [&](unsigned c) {
+        const unsigned base = c << kPartChunkShift;
 #pragma unroll
         for (int r = 0; r < kPartPer; ++r) {
             const unsigned i = base + r * kPartThreads + t;
             y[r] = (c < G.nchunks && i < n) ? ld_stream(P.coords[1] + (size_t)i * P.coord_stride) : T(0);
         }
     };
-    request_xy(blockIdx.x);
+    request_x(blockIdx.x);
+    request_y(blockIdx.x);
     for (unsigned c = blockIdx.x; c < G.nchunks; c += gridDim.x) {
     const unsigned base = c << kPartChunkShift;
     if (t < (unsigned)kPartMaxLists) s_cnt[t] = 0u;
@@ -186,6 +193,9 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_scatter_kernel(const __g
             G.pos[i] = (unsigned short)pk[r];
         }
     }
+#if NINT_PART_EARLY_X
+    request_x(c + gridDim.x);  // the first column of the next chunk: its registers are free, and the classification is what waits for it
+#endif
     {
         T z[kPartPer];
 #pragma unroll
@@ -207,7 +217,10 @@ __global__ void __launch_bounds__(kPartThreads, 2) part_scatter_kernel(const __g
         for (int d = 0; d < 3; ++d) bulk_store(G.rec[d] + base, s_rec + d * kPartChunk, kPartChunk * (unsigned)sizeof(T));
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    request_xy(c + gridDim.x);
+#if !NINT_PART_EARLY_X
+    request_x(c + gridDim.x);
+#endif
+    request_y(c + gridDim.x);
     if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();  // the staged chunk has been read: the next one may be written
     }
