@@ -134,12 +134,12 @@ class _InterpBase:
 
     def last_query_order(self) -> int:
         """Diagnostics: route of the most recent batch (0 no order probe ran, 1 coherent: single pass on the
-        cell-packed table, 2 incoherent: binned tiles or slab passes).  Synchronises the device."""
+        cell-packed table, 2 incoherent: slab lists, slab passes or binned tiles).  Synchronises the device."""
         return int(L.lib().nint_last_query_order(self._h))
 
     def last_incoherent_route(self) -> int:
         """Diagnostics: what the most recent batch enqueued for an incoherent verdict (0 nothing, 1 slab passes on
-        the plain table, 2 binned tiles staged in shared memory by TMA)."""
+        the plain table, 2 binned tiles staged in shared memory by TMA, 3 slab lists on the cell-packed table)."""
         return int(L.lib().nint_last_incoherent_route(self._h))
 
     # -- batch entry points (new) ----------------------------------------------------------------

@@ -31,11 +31,14 @@ def kernels(path):
 
 def main():
     commit = sys.argv[1]
+    # optional: --only key,key  (re)writes just those profile files (the others in gpurun_out/ are an earlier capture)
+    only = set(sys.argv[sys.argv.index("--only") + 1].split(",")) if "--only" in sys.argv else None
+    earlier = sys.argv[sys.argv.index("--earlier") + 1] if "--earlier" in sys.argv else None  # commit of that earlier capture
     out = ROOT / "gpurun_out"
     prof = ROOT / "profiles"
     for key, name in NAMES.items():
         summ = out / f"r2p_summary_{key}.txt"
-        if not summ.exists():
+        if not summ.exists() or (only is not None and key not in only):
             continue
         plain = (out / f"r2p_plain_{key}.log").read_text().strip().splitlines()
         text = [f"# ncu --set full --clock-control none --import-source on, B200, round 2, captured at commit {commit} (tools/gpu_profiles.sh)",
@@ -75,6 +78,7 @@ def main():
                   "1e9 points: the slab lists are scaled from a 2.6e8-point capture (scatter + evaluate + merge); the slab route is the order "
                   "probe + 3 slab_kernel passes; the binned-tiles figure is scaled from a 2.6e8-point capture (bin + evaluate); the single-pass figure on random queries is the round-1 capture (that kernel's random path is unchanged)",
           "commit": commit, "kernel_source_sha": bench.kernel_source_sha(), "algorithmic_bytes_per_launch": 32e9,
+          **({"other_routes_captured_at": earlier + " (their kernels are unchanged since)"} if earlier else {}),
           "interp3d_linear_f64_uniform_random_lists_bytes_per_call": sum(tot(k) for k in lists) * 1e9 / 2.6e8,
           "interp3d_linear_f64_uniform_random_slab_bytes_per_call": sum(tot(k) for k in slab),
           "interp3d_linear_f64_uniform_random_slab_bytes_per_pass": tot(slab[0]),
