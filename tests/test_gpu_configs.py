@@ -105,6 +105,16 @@ def test_config4_interpnd_f32_n5_wrap_fill():
     _run(1, axes, v, LIN, WRAP, cols, dtype=np.float32)
     _run(1, axes, v, LIN, FILL, cols, dtype=np.float32, fill=-1.0)
     _run(1, axes, v, NEA, WRAP, cols, dtype=np.float32)
+    # at 6e6 points the default route of an incoherent batch under Wrap is the slab lists with five columns (nint_part.cuh)
+    from gpu_util import assert_same, gpu_eval, make_pair
+
+    from ninterp_b200 import _lib
+
+    cols = [rng.uniform(a[0] - 0.25 * (a[-1] - a[0]), a[-1] + 0.25 * (a[-1] - a[0]), 6_000_000).astype(np.float32) for a in axes]
+    g, o = make_pair(1, axes, v, LIN, WRAP, dtype=np.float32)
+    got, st, _ = gpu_eval(g, cols)
+    assert _lib.lib().nint_last_query_order(g._h) == 2 and _lib.lib().nint_last_incoherent_route(g._h) == 3
+    assert_same(got, st, *o.eval(cols, nthreads=O.max_threads()), "config 4 under Wrap, slab lists")
 
 
 def test_config5_enable_mixed_and_1d_index_strategies():
